@@ -1,0 +1,255 @@
+// Device code shared by the forward and backward radiance-field kernels: sample loading,
+// multi-resolution hash-grid gathers (tcnn grid.h semantics), vector lerps
+// (tensor_composition.cu:30-45), shared-memory operand layouts for tcgen05.mma.
+#pragma once
+#include "common.cuh"
+
+namespace hrf {
+
+constexpr int kTile = 128;              // samples per CTA tile == UMMA M
+constexpr uint32_t kPrimeY = 2654435761u;  // tcnn coherent_prime_hash
+constexpr uint32_t kPrimeZ = 805459861u;
+
+// Byte offsets of the packed bf16 weight blob (UMMA K-major SWIZZLE_NONE core-matrix layout,
+// element (n,k) of W[N,K] at ((k/8)*(N/8) + n/8)*128 + (n%8)*16 + (k%8)*2).
+constexpr uint32_t kWSig1 = 0;       // sigma  W1 [64,32]
+constexpr uint32_t kWSig2 = 4096;    // sigma  W2 [16,64]
+constexpr uint32_t kWCol1 = 6144;    // colour W1 [64,32]
+constexpr uint32_t kWCol2 = 10240;   // colour W2 [64,64]
+constexpr uint32_t kWCol3 = 18432;   // colour W3 [16,64]
+constexpr uint32_t kWBlobBytes = HRF_MLP_BLOB_BYTES;
+// row-major fp32 gradient buffer offsets (elements)
+constexpr int kGSig1 = 0, kGSig2 = 2048, kGCol1 = 3072, kGCol2 = 5120, kGCol3 = 9216, kGTotal = 10240;
+
+// A-operand tile: 128 rows x K bf16, K-major SWIZZLE_NONE: element (r,k) at
+// (k/8)*kAChunk + (r/8)*128 + (r%8)*16 + (k%8)*2   -> LBO = kAChunk (K direction), SBO = 128 (M direction).
+constexpr uint32_t kAChunk = (kTile / 8) * 128;  // 2048
+
+__device__ __forceinline__ uint32_t a_row_off(int r) { return (uint32_t)(r >> 3) * 128u + (uint32_t)(r & 7) * 16u; }
+__device__ __forceinline__ uint32_t w_off(int n, int k, int N) {
+  return (uint32_t)((k >> 3) * (N >> 3) + (n >> 3)) * 128u + (uint32_t)(n & 7) * 16u + (uint32_t)(k & 7) * 2u;
+}
+
+struct FieldArgs {
+  hrf_field f;
+  hrf_samples s;
+  float* sigma;
+  uint32_t* geo;   // bf16 [N,16] viewed as u32 pairs
+  float* rgb;
+  uint4* feat;     // bf16 [N,32] composed features (optional output)
+  int mode;
+};
+
+struct Sample {
+  float x, y, z, t;        // normalised coordinates in [0,1] (positions + 0.5, local time)
+  float dx, dy, dz;        // view direction
+  const hrf_segment* seg;  // segment descriptor (NULL for padding threads)
+};
+
+__device__ __forceinline__ Sample load_sample(const hrf_field& f, const hrf_samples& s, int64_t i, bool need_dir) {
+  Sample o;
+  o.seg = nullptr;
+  o.x = o.y = o.z = o.t = 0.f;
+  o.dx = o.dy = o.dz = 0.f;
+  if (i >= s.num_samples) return o;
+  int frame;
+  float px, py, pz;
+  if (s.ray_origins != nullptr) {
+    // volume_rendering.py:66-69 : positions = origins[ri] + t * dirs[ri]  (mul, then add: two roundings)
+    const int64_t r = __ldg(s.ray_indices + i);
+    const float t = __ldg(s.sample_distances + i);
+    const float* ro = s.ray_origins + 3 * r;
+    const float* rd = s.ray_directions + 3 * r;
+    o.dx = __ldg(rd), o.dy = __ldg(rd + 1), o.dz = __ldg(rd + 2);
+    px = __fadd_rn(__ldg(ro), __fmul_rn(t, o.dx));
+    py = __fadd_rn(__ldg(ro + 1), __fmul_rn(t, o.dy));
+    pz = __fadd_rn(__ldg(ro + 2), __fmul_rn(t, o.dz));
+    frame = __ldg(s.ray_frame_numbers + r);
+  } else {
+    px = __ldg(s.positions + 3 * i), py = __ldg(s.positions + 3 * i + 1), pz = __ldg(s.positions + 3 * i + 2);
+    if (need_dir && s.directions != nullptr) {
+      o.dx = __ldg(s.directions + 3 * i), o.dy = __ldg(s.directions + 3 * i + 1), o.dz = __ldg(s.directions + 3 * i + 2);
+    }
+    frame = __ldg(s.frame_numbers + i);
+  }
+  // humanrf.py:175 : positions + 0.5 ; :176 normalised local frame number
+  o.x = __fadd_rn(px, 0.5f), o.y = __fadd_rn(py, 0.5f), o.z = __fadd_rn(pz, 0.5f);
+  int sg = -1;
+  if (frame >= 0 && frame < f.lut_size) {
+    sg = __ldg(f.frame_to_segment + frame);
+    o.t = __ldg(f.frame_to_tlocal + frame);
+  }
+  if (sg >= 0 && sg < f.num_segments) o.seg = f.segments + sg;
+  return o;
+}
+
+struct Cell {
+  uint32_t g;
+  float f;
+};
+__device__ __forceinline__ Cell to_cell(float scale, float v) {
+  // tcnn pos_fract: pos = fmaf(scale, x, 0.5); grid = (uint32_t)(int)floorf(pos); frac = pos - floor
+  const float p = __fmaf_rn(scale, v, 0.5f);
+  const float fl = floorf(p);
+  Cell c;
+  c.g = (uint32_t)(int)fl;
+  c.f = p - fl;
+  return c;
+}
+
+// Eight corner indices of one level (tcnn grid_index): dense x + y*res + z*res^2, or the
+// coherent prime hash, both reduced modulo the level's hashmap size.
+__device__ __forceinline__ void corner_indices(bool hashed, uint32_t res, uint32_t size, Cell a, Cell b, Cell c,
+                                               uint32_t idx[8]) {
+  if (hashed) {
+    const uint32_t m = size - 1u;  // hashed levels always have size == 2^log2T
+    const uint32_t b0 = b.g * kPrimeY, b1 = (b.g + 1u) * kPrimeY;
+    const uint32_t c0 = c.g * kPrimeZ, c1 = (c.g + 1u) * kPrimeZ;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      idx[k] = (((k & 1) ? a.g + 1u : a.g) ^ ((k & 2) ? b1 : b0) ^ ((k & 4) ? c1 : c0)) & m;
+  } else {
+    const uint32_t r2 = res * res;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      uint32_t v = ((k & 1) ? a.g + 1u : a.g) + ((k & 2) ? b.g + 1u : b.g) * res + ((k & 4) ? c.g + 1u : c.g) * r2;
+      if (v >= size) {
+        v -= size;
+        if (v >= size) v %= size;
+      }
+      idx[k] = v;
+    }
+  }
+}
+__device__ __forceinline__ void corner_weights(Cell a, Cell b, Cell c, float w[8]) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float v = (k & 1) ? a.f : 1.f - a.f;   // weight = 1; weight *= ... per dim, in dim order
+    v *= (k & 2) ? b.f : 1.f - b.f;
+    v *= (k & 4) ? c.f : 1.f - c.f;
+    w[k] = v;
+  }
+}
+
+// Trilinear gather of one level of one grid -> 2 features (fp32 blend of bf16 entries).
+__device__ __forceinline__ float2 gather_level(const uint32_t* __restrict__ tab, bool hashed, uint32_t res,
+                                               uint32_t size, Cell a, Cell b, Cell c) {
+  uint32_t idx[8], raw[8];
+  float w[8];
+  corner_indices(hashed, res, size, a, b, c, idx);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) raw[k] = __ldg(tab + idx[k]);
+  corner_weights(a, b, c, w);
+  float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    acc.x = __fmaf_rn(w[k], bf16_lo(raw[k]), acc.x);
+    acc.y = __fmaf_rn(w[k], bf16_hi(raw[k]), acc.y);
+  }
+  return acc;
+}
+
+// 1-D lerp taps into `vectors` (tensor_composition.cu:37-45)
+struct VecTap {
+  uint32_t o0, o1;  // element offsets of row i0 / i1 inside vectors[axis]
+  float frac;
+};
+__device__ __forceinline__ VecTap make_tap(float coord, int vec_res, int axis) {
+  const float c = __fmaf_rn(coord, (float)vec_res, -0.5f);
+  const float fl = floorf(c);
+  VecTap t;
+  t.frac = c - fl;
+  const int i0 = (int)fmaxf(fl, 0.f);
+  const int i1 = (int)fminf(fl + 1.f, (float)(vec_res - 1));
+  t.o0 = ((uint32_t)axis * (uint32_t)vec_res + (uint32_t)min(max(i0, 0), vec_res - 1)) * HRF_N_FEATURES;
+  t.o1 = ((uint32_t)axis * (uint32_t)vec_res + (uint32_t)min(max(i1, 0), vec_res - 1)) * HRF_N_FEATURES;
+  return t;
+}
+__device__ __forceinline__ float2 lerp_tap(const float* __restrict__ vec, const VecTap& t, int feat) {
+  const float2 v0 = __ldg(reinterpret_cast<const float2*>(vec + t.o0 + feat));
+  const float2 v1 = __ldg(reinterpret_cast<const float2*>(vec + t.o1 + feat));
+  return make_float2(v0.x + t.frac * (v1.x - v0.x), v0.y + t.frac * (v1.y - v0.y));
+}
+
+// Degree-4 real spherical harmonics of the view direction (tcnn SphericalHarmonics on (d+1)/2).
+__device__ __forceinline__ void sh4(float dx, float dy, float dz, float* o) {
+  const float x = ((dx + 1.f) * 0.5f) * 2.f - 1.f, y = ((dy + 1.f) * 0.5f) * 2.f - 1.f,
+              z = ((dz + 1.f) * 0.5f) * 2.f - 1.f;
+  const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+  o[0] = 0.28209479177387814f;
+  o[1] = -0.48860251190291987f * y;
+  o[2] = 0.48860251190291987f * z;
+  o[3] = -0.48860251190291987f * x;
+  o[4] = 1.0925484305920792f * xy;
+  o[5] = -1.0925484305920792f * yz;
+  o[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
+  o[7] = -1.0925484305920792f * xz;
+  o[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
+  o[9] = 0.59004358992664352f * y * (-3.0f * x2 + y2);
+  o[10] = 2.8906114426405538f * xy * z;
+  o[11] = 0.45704579946446572f * y * (1.0f - 5.0f * z2);
+  o[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
+  o[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2);
+  o[14] = 1.4453057213202769f * z * (x2 - y2);
+  o[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
+}
+
+// Encode one sample (4 grids x 16 levels, composed with the vector lerps) and write the 32
+// bf16 features of row `row` into the K-major A tile at `abuf` (shared memory).
+__device__ __forceinline__ void encode_to_smem(const hrf_field& f, const Sample& s, unsigned char* abuf, int row) {
+  const uint32_t roff = a_row_off(row);
+  if (s.seg == nullptr) {
+#pragma unroll
+    for (int kg = 0; kg < 4; ++kg) *reinterpret_cast<uint4*>(abuf + kg * kAChunk + roff) = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  const hrf_segment* sg = s.seg;
+  const uint32_t* g0 = sg->grid[0];
+  const uint32_t* g1 = sg->grid[1];
+  const uint32_t* g2 = sg->grid[2];
+  const uint32_t* g3 = sg->grid[3];
+  const float* vec = sg->vectors;
+  const uint32_t hmask = sg->hashed_mask;
+  const VecTap tx = make_tap(s.x, f.vec_res, 0), ty = make_tap(s.y, f.vec_res, 1), tz = make_tap(s.z, f.vec_res, 2),
+               tt = make_tap(s.t, f.vec_res, 3);
+#pragma unroll 1
+  for (int kg = 0; kg < 4; ++kg) {
+    uint32_t pk[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int l = kg * 4 + j;
+      const float scale = f.level_scale[l];
+      const uint32_t res = f.level_res[l];
+      const uint32_t off = sg->level_offset[l];
+      const uint32_t size = sg->level_size[l];
+      const bool hashed = (hmask >> l) & 1u;
+      const Cell cx = to_cell(scale, s.x), cy = to_cell(scale, s.y), cz = to_cell(scale, s.z),
+                 ct = to_cell(scale, s.t);
+      // decomposition4d.py:126-129 : xyz, xyt, yzt, xzt
+      const float2 e0 = gather_level(g0 + off, hashed, res, size, cx, cy, cz);
+      const float2 e1 = gather_level(g1 + off, hashed, res, size, cx, cy, ct);
+      const float2 e2 = gather_level(g2 + off, hashed, res, size, cy, cz, ct);
+      const float2 e3 = gather_level(g3 + off, hashed, res, size, cx, cz, ct);
+      const float2 vx = lerp_tap(vec, tx, 2 * l), vy = lerp_tap(vec, ty, 2 * l), vz = lerp_tap(vec, tz, 2 * l),
+                   vt = lerp_tap(vec, tt, 2 * l);
+      // tensor_composition.cu:49-52 : xyz*v_t + xyt*v_z + yzt*v_x + xzt*v_y
+      const float o0 = e0.x * vt.x + e1.x * vz.x + e2.x * vx.x + e3.x * vy.x;
+      const float o1 = e0.y * vt.y + e1.y * vz.y + e2.y * vx.y + e3.y * vy.y;
+      pk[j] = pack_bf16x2(o0, o1);
+    }
+    *reinterpret_cast<uint4*>(abuf + kg * kAChunk + roff) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
+
+// Issue one dense layer D[128,N] = A[128,K] * W[N,K]^T on the tensor cores (one thread).
+__device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a_addr, uint32_t w_addr, int N, int K) {
+  const uint32_t idesc = make_idesc_bf16(kTile, N);
+  const uint32_t b_lbo = (uint32_t)(N >> 3) * 128u;
+  for (int k = 0; k < K / 16; ++k) {
+    const uint64_t ad = make_smem_desc(a_addr + (uint32_t)k * 2u * kAChunk, kAChunk, 128u);
+    const uint64_t bd = make_smem_desc(w_addr + (uint32_t)k * 2u * b_lbo, b_lbo, 128u);
+    umma_bf16(tmem_d, ad, bd, idesc, k > 0 ? 1u : 0u);
+  }
+}
+
+}  // namespace hrf

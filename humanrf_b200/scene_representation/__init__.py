@@ -1,0 +1,2 @@
+from .humanrf import HumanRF  # noqa: F401
+from .query_io import QueryInput, QueryOutput  # noqa: F401

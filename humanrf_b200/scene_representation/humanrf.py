@@ -1,0 +1,325 @@
+"""HumanRF scene representation backed by the fused sm_100a kernels.
+
+Drop-in for humanrf/scene_representation/humanrf.py:14-220 (+ decomposition4d.py:41-135): same
+constructor kwargs, ``density`` / ``forward`` / ``get_params``, same state-dict keys
+
+    feature_grids.{s}.vectors                              [4, 2048, 32] fp32
+    feature_grids.{s}.{xyz,xyt,yzt,xzt}_encoding.params    flat fp32 (tcnn layout: level-major, 2 features/entry)
+    sigma_net.params / color_net.params                    flat fp32 (tcnn FullyFusedMLP row-major [out,in] per layer)
+    frame_numbers_to_segment_numbers / frame_numbers_to_normalized_local_frame_numbers (buffers)
+
+so checkpoints written by the reference trainer load unchanged (trainer.py:528-620).  What is
+different by design: tables are read by the kernels from bf16 shadow copies of the fp32 master
+parameters (refreshed whenever a parameter's version changes); all segments stay resident in
+HBM (the reference off-loads idle segments to the host, humanrf.py:169-179 -- pointless with
+180 GB); encode -> MLP runs in one kernel instead of 4 tcnn encodings + compose + 2 tcnn nets.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from .. import _lib as L
+from .grid_layout import (MLP_COLOR_PARAMS, MLP_SIGMA_PARAMS, GridLayout, mlp_blob_permutation,
+                          segment_log2_hashmap_size)
+from .query_io import QueryInput, QueryOutput
+
+GRID_NAMES = ("xyz_encoding", "xyt_encoding", "yzt_encoding", "xzt_encoding")  # decomposition4d.py:126-129
+
+
+class _FlatParams(torch.nn.Module):
+    """Stands in for a tcnn module: a single flat fp32 ``params`` (tcnn bindings/torch/modules.py)."""
+
+    def __init__(self, init: torch.Tensor):
+        super().__init__()
+        self.params = torch.nn.Parameter(init)
+
+
+class Decomposition4D(torch.nn.Module):
+    """Parameter container mirroring decomposition4d.py:41-122 (4 hash grids + 4 dense 1-D vector tables)."""
+
+    def __init__(self, ngp_n_levels=16, ngp_n_features_per_level=2, ngp_log2_hashmap_size=19, ngp_base_resolution=32,
+                 ngp_finest_resolution=2048, vectors_finest_resolution=2048):
+        super().__init__()
+        if ngp_n_levels != 16 or ngp_n_features_per_level != 2:
+            raise NotImplementedError("the sm_100a kernels are specialised for n_levels=16, n_features_per_level=2")
+        self.layout = GridLayout(ngp_log2_hashmap_size, ngp_n_levels, ngp_base_resolution, ngp_finest_resolution)
+        feature_size = ngp_n_levels * ngp_n_features_per_level
+        self.vectors = torch.nn.Parameter(torch.randn((4, vectors_finest_resolution, feature_size)) * 0.1)  # :76-78
+        for name in GRID_NAMES:
+            # tcnn GridEncoding initialises U(-1e-4, 1e-4)
+            init = (torch.rand(self.layout.n_params) * 2 - 1) * 1e-4
+            setattr(self, name, _FlatParams(init))
+
+    def grids(self) -> List[torch.nn.Parameter]:
+        return [getattr(self, n).params for n in GRID_NAMES]
+
+
+def _xavier_flat(shapes, gen=None) -> torch.Tensor:
+    out = []
+    for o, i in shapes:
+        a = float(np.sqrt(6.0 / (i + o)))
+        out.append(((torch.rand((o, i), generator=gen) * 2 - 1) * a).reshape(-1))
+    return torch.cat(out)
+
+
+class HumanRF(torch.nn.Module):
+    def __init__(self, density_scale: float, sorted_frame_numbers: Tuple[int, ...], n_features_per_level: int,
+                 log2_hashmap_size: int, n_levels: int, coarsest_resolution: int, finest_resolution: int,
+                 geometry_feature_dim: int, n_neurons: int, n_hidden_layers_density: int, n_hidden_layers_color: int,
+                 sh_degree: int, segment_sizes: Tuple[int, ...], camera_embedding_dim: int, **kwargs):
+        super().__init__()
+        if (n_neurons, geometry_feature_dim, n_hidden_layers_density, n_hidden_layers_color, sh_degree) != (64, 15, 1, 2, 4):
+            raise NotImplementedError(
+                "the fused sm_100a kernel is specialised for the reference defaults (model_args.py:10-19): "
+                "n_neurons=64, geometry_feature_dim=15, 1/2 hidden layers, sh_degree=4")
+        if camera_embedding_dim != 0:
+            raise NotImplementedError("camera_embedding_dim > 0 is not implemented yet (paper setting is 0)")
+        self.density_scale = float(density_scale)
+        self.num_frames = len(sorted_frame_numbers)
+        self.num_segments = len(segment_sizes)
+        self.camera_embedding_dim = camera_embedding_dim
+
+        # humanrf.py:79-103
+        end = np.cumsum(segment_sizes, dtype=np.int32)
+        end[-1] = min(end[-1], self.num_frames)
+        start = np.concatenate((np.zeros(1, dtype=np.int32), end[:-1]))
+        f2s = np.full((sorted_frame_numbers[-1] + 1), fill_value=-1, dtype=np.int32)
+        f2t = np.full((sorted_frame_numbers[-1] + 1), fill_value=-1, dtype=np.float32)
+        for s in range(self.num_segments):
+            frames = [sorted_frame_numbers[j] for j in range(start[s], end[s])]
+            for local, frame in enumerate(frames):
+                f2s[frame] = s
+                f2t[frame] = local / len(frames)
+        self.register_buffer("frame_numbers_to_segment_numbers", torch.from_numpy(f2s))
+        self.register_buffer("frame_numbers_to_normalized_local_frame_numbers", torch.from_numpy(f2t))
+
+        self.feature_grids = torch.nn.ModuleList()
+        for segment_size in segment_sizes:
+            self.feature_grids.append(Decomposition4D(
+                ngp_n_levels=n_levels, ngp_n_features_per_level=n_features_per_level,
+                ngp_log2_hashmap_size=segment_log2_hashmap_size(segment_size, log2_hashmap_size),
+                ngp_base_resolution=coarsest_resolution, ngp_finest_resolution=finest_resolution,
+                vectors_finest_resolution=finest_resolution))
+        self.total_feature_dim = n_levels * n_features_per_level
+        self.sigma_net = _FlatParams(_xavier_flat([(64, 32), (16, 64)]))
+        self.color_net = _FlatParams(_xavier_flat([(64, 32), (64, 64), (16, 64)]))
+        assert self.sigma_net.params.numel() == MLP_SIGMA_PARAMS and self.color_net.params.numel() == MLP_COLOR_PARAMS
+        self._native: Optional[_NativeField] = None
+
+    # ------------------------------------------------------------------ reference API
+    def density(self, query_input: QueryInput) -> QueryOutput:
+        sigma, geo, _ = _FieldFunction.apply(self, 0, query_input.positions, None, query_input.frame_numbers,
+                                             *self.hot_parameters())
+        return QueryOutput(density=sigma, geometry_features=geo)
+
+    def forward(self, query_input: QueryInput) -> QueryOutput:
+        sigma, geo, rgb = _FieldFunction.apply(self, 1, query_input.positions, query_input.directions,
+                                               query_input.frame_numbers, *self.hot_parameters())
+        return QueryOutput(density=sigma, geometry_features=geo, radiance=rgb)
+
+    def get_params(self, lr):
+        return [
+            {'params': self.feature_grids.parameters(), 'lr': lr},
+            {'params': self.sigma_net.parameters(), 'lr': lr},
+            {'params': self.color_net.parameters(), 'lr': lr},
+        ]
+
+    # ------------------------------------------------------------------ native plumbing
+    def hot_parameters(self) -> List[torch.nn.Parameter]:
+        """Per segment: 4 grids + vectors; then sigma and colour MLP parameters (gradient order)."""
+        ps: List[torch.nn.Parameter] = []
+        for fg in self.feature_grids:
+            ps += fg.grids() + [fg.vectors]
+        return ps + [self.sigma_net.params, self.color_net.params]
+
+    def native(self) -> "_NativeField":
+        if self._native is None:
+            self._native = _NativeField(self)
+        self._native.refresh()
+        return self._native
+
+
+class _NativeField:
+    """Device-side view of a HumanRF module: bf16 shadow tables, packed MLP blob, descriptors."""
+
+    def __init__(self, model: HumanRF):
+        self.model = model
+        self.keys = None
+        self.versions = None
+        self.shadows: List[torch.Tensor] = []
+        self.blob: Optional[torch.Tensor] = None
+        self.perm: Optional[torch.Tensor] = None
+        self.seg_dev: Optional[torch.Tensor] = None
+        self.field = L.Field()
+
+    def _device(self) -> torch.device:
+        dev = self.model.sigma_net.params.device
+        if dev.type != "cuda":
+            raise RuntimeError("humanrf_b200: the scene representation must live on a CUDA device "
+                               "(there is no CPU path); call .to('cuda') first")
+        return dev
+
+    def refresh(self) -> None:
+        m = self.model
+        dev = self._device()
+        params = m.hot_parameters()
+        keys = tuple(p.data_ptr() for p in params) + (m.frame_numbers_to_segment_numbers.data_ptr(),)
+        rebuild = keys != self.keys
+        lib = L.lib()
+        if rebuild:
+            for p in params:
+                if p.device != dev or p.dtype != torch.float32 or not p.is_contiguous():
+                    raise RuntimeError("humanrf_b200: parameters must be contiguous fp32 CUDA tensors on one device")
+            self.shadows = []
+            for fg in m.feature_grids:
+                self.shadows.append([torch.empty(g.numel(), dtype=torch.bfloat16, device=dev) for g in fg.grids()])
+            self.blob = torch.empty(L.MLP_BLOB_BYTES // 2, dtype=torch.bfloat16, device=dev)
+            self.perm = torch.from_numpy(mlp_blob_permutation()).to(dev)
+            segs = (L.Segment * m.num_segments)()
+            for s, fg in enumerate(m.feature_grids):
+                lay = fg.layout
+                for k in range(4):
+                    segs[s].grid[k] = self.shadows[s][k].data_ptr()
+                segs[s].vectors = fg.vectors.data_ptr()
+                for l in range(16):
+                    segs[s].level_offset[l] = int(lay.offset[l])
+                    segs[s].level_size[l] = int(lay.size[l])
+                segs[s].hashed_mask = lay.hashed_mask
+                segs[s].n_entries = lay.n_entries
+            raw = np.frombuffer(bytes(segs), dtype=np.uint8).copy()
+            self.seg_dev = torch.from_numpy(raw).to(dev)
+            lay0 = m.feature_grids[0].layout
+            f = self.field
+            f.segments = self.seg_dev.data_ptr()
+            f.frame_to_segment = m.frame_numbers_to_segment_numbers.data_ptr()
+            f.frame_to_tlocal = m.frame_numbers_to_normalized_local_frame_numbers.data_ptr()
+            f.mlp_blob = self.blob.data_ptr()
+            for l in range(16):
+                f.level_scale[l] = float(lay0.scale[l])
+                f.level_res[l] = int(lay0.res[l])
+            f.num_segments = m.num_segments
+            f.lut_size = m.frame_numbers_to_segment_numbers.numel()
+            f.vec_res = m.feature_grids[0].vectors.shape[1]
+            f.density_scale = m.density_scale
+            self.keys = keys
+            self.versions = None
+        versions = tuple(p._version for p in params)
+        if versions != self.versions:
+            old = self.versions
+            with torch.no_grad():
+                i = 0
+                for s, fg in enumerate(m.feature_grids):
+                    for k, g in enumerate(fg.grids()):
+                        if old is None or old[i] != versions[i]:
+                            L.check(lib.hrf_cast_bf16(g.data_ptr(), self.shadows[s][k].data_ptr(), g.numel(), L.stream()))
+                        i += 1
+                    i += 1  # vectors are read as fp32 directly
+                if old is None or old[-2:] != versions[-2:]:
+                    flat = torch.cat((m.sigma_net.params.detach(), m.color_net.params.detach()))
+                    self.blob.copy_(flat[self.perm].to(torch.bfloat16))
+            self.versions = versions
+
+    def mark_shadows_current(self) -> None:
+        """Called by the fused optimiser, which writes the shadows itself."""
+        self.versions = tuple(p._version for p in self.model.hot_parameters())
+
+    # -------------------------------------------------------------------------------------
+    def samples_query(self, positions, directions, frame_numbers) -> L.Samples:
+        s = L.Samples()
+        s.positions = positions.data_ptr()
+        s.directions = None if directions is None else directions.data_ptr()
+        s.frame_numbers = frame_numbers.data_ptr()
+        s.num_samples = positions.shape[0]
+        return s
+
+    def samples_rays(self, ray_origins, ray_directions, ray_frames, distances, ray_indices) -> L.Samples:
+        s = L.Samples()
+        s.ray_origins = ray_origins.data_ptr()
+        s.ray_directions = ray_directions.data_ptr()
+        s.ray_frame_numbers = ray_frames.data_ptr()
+        s.sample_distances = distances.data_ptr()
+        s.ray_indices = ray_indices.data_ptr()
+        s.num_samples = distances.shape[0]
+        return s
+
+    def forward(self, samples: L.Samples, mode: int, want_geo: bool, want_feat: bool, mlp_impl: int = 0):
+        dev = self._device()
+        n = int(samples.num_samples)
+        sigma = torch.empty(n, dtype=torch.float32, device=dev)
+        geo = torch.empty((n, 16), dtype=torch.bfloat16, device=dev) if want_geo else None
+        rgb = torch.empty((n, 3), dtype=torch.float32, device=dev) if mode == 1 else None
+        feat = torch.empty((n, 32), dtype=torch.bfloat16, device=dev) if want_feat else None
+        L.check(L.lib().hrf_field_forward(C.byref(self.field), C.byref(samples), mode, mlp_impl, sigma.data_ptr(),
+                                          L.ptr(geo), L.ptr(rgb), L.ptr(feat), L.stream()))
+        return sigma, geo, rgb, feat
+
+    def backward(self, samples: L.Samples, d_sigma, d_rgb, feat, grad_tensors: List[torch.Tensor]):
+        """grad_tensors: fp32 buffers in hot_parameters() order (accumulated into)."""
+        m = self.model
+        dev = self._device()
+        sg = (L.SegmentGrads * m.num_segments)()
+        i = 0
+        for s in range(m.num_segments):
+            for k in range(4):
+                sg[s].grid[k] = grad_tensors[i].data_ptr()
+                i += 1
+            sg[s].vectors = grad_tensors[i].data_ptr()
+            i += 1
+        sg_dev = torch.from_numpy(np.frombuffer(bytes(sg), dtype=np.uint8).copy()).to(dev)
+        d_mlp = torch.zeros(L.MLP_GRAD_ELEMS, dtype=torch.float32, device=dev)
+        L.check(L.lib().hrf_field_backward(C.byref(self.field), C.byref(samples), sg_dev.data_ptr(), L.ptr(d_sigma),
+                                           L.ptr(d_rgb), L.ptr(feat), d_mlp.data_ptr(), L.stream()))
+        grad_tensors[i].add_(d_mlp[:MLP_SIGMA_PARAMS])
+        grad_tensors[i + 1].add_(d_mlp[MLP_SIGMA_PARAMS:])
+        return sg_dev  # keep alive until the kernel has run (stream-ordered free is safe, but be explicit)
+
+
+def _as_f32c(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.float32).contiguous()
+
+
+def _as_frames(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().reshape(-1).to(torch.int32).contiguous()
+
+
+class _FieldFunction(torch.autograd.Function):
+    """autograd wrapper of the fused kernels in QueryInput form (humanrf.py:158-208)."""
+
+    @staticmethod
+    def forward(ctx, model: HumanRF, mode: int, positions, directions, frame_numbers, *params):
+        nat = model.native()
+        pos = L.require_cuda(_as_f32c(positions), "positions")
+        dirs = None if directions is None else L.require_cuda(_as_f32c(directions), "directions")
+        frames = L.require_cuda(_as_frames(frame_numbers), "frame_numbers")
+        needs_grad = any(ctx.needs_input_grad[5:])
+        samples = nat.samples_query(pos, dirs, frames)
+        sigma, geo, rgb, feat = nat.forward(samples, mode, want_geo=True, want_feat=needs_grad)
+        ctx.model, ctx.mode = model, mode
+        ctx.save_for_backward(pos, dirs if dirs is not None else pos, frames, feat if feat is not None else pos)
+        ctx.has_dirs = dirs is not None
+        geo_out = geo[:, 1:]
+        ctx.mark_non_differentiable(geo_out)
+        if rgb is None:
+            rgb = sigma.new_zeros((0, 3))
+            ctx.mark_non_differentiable(rgb)
+        return sigma, geo_out, rgb
+
+    @staticmethod
+    def backward(ctx, d_sigma, d_geo, d_rgb):
+        model = ctx.model
+        pos, dirs, frames, feat = ctx.saved_tensors
+        nat = model.native()
+        params = model.hot_parameters()
+        grads = [torch.zeros_like(p) for p in params]
+        samples = nat.samples_query(pos, dirs if ctx.has_dirs else None, frames)
+        ds = None if d_sigma is None else _as_f32c(d_sigma)
+        dr = None if (d_rgb is None or ctx.mode == 0) else _as_f32c(d_rgb)
+        if ds is None:
+            ds = torch.zeros(pos.shape[0], dtype=torch.float32, device=pos.device)
+        keep = nat.backward(samples, ds, dr, feat, grads)
+        del keep
+        return (None, None, None, None, None, *grads)

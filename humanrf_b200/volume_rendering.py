@@ -1,0 +1,137 @@
+"""Volume renderer on the fused sm_100a kernels.
+
+Drop-in for humanrf/volume_rendering.py:14-150: ``RenderOutput``, ``prune_samples`` (in-place,
+returns None) and ``render`` with the reference signatures.  Differences by design:
+
+* positions / directions / frame numbers are never materialised per sample: the field kernel
+  reads ``sample_distances`` + ``ray_indices`` and the per-ray arrays directly (the reference
+  builds three [N,3] gathers per call, volume_rendering.py:66-72,110-119);
+* nerfacc's scan-by-key / scatter-add are replaced by one warp-per-ray kernel
+  (csrc/composite.cu); pruning compacts on the device and reads back one counter.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List
+
+import torch
+
+from . import _lib as L
+from .dataset.input_batch import InputBatch
+from .scene_representation.humanrf import HumanRF
+
+
+@dataclass
+class RenderOutput:
+    # (#rays x 3): [torch.float]
+    color: torch.Tensor = None
+    # (#rays x 1): [torch.float]
+    weights_sum: torch.Tensor = None
+
+    @classmethod
+    @torch.no_grad()
+    def merge_render_outputs(cls, render_outputs: List["RenderOutput"]) -> "RenderOutput":
+        out = RenderOutput()
+        for key, val in vars(render_outputs[0]).items():
+            if isinstance(val, torch.Tensor):
+                setattr(out, key, torch.cat([getattr(r, key) for r in render_outputs], dim=0))
+            elif val is not None:
+                raise RuntimeError("Unknown data type in the input_batches!")
+        return out
+
+
+def _ray_arrays(ib: InputBatch):
+    o = L.require_cuda(ib.ray_origins.detach().float().contiguous(), "ray_origins")
+    d = L.require_cuda(ib.ray_directions.detach().float().contiguous(), "ray_directions")
+    fr = L.require_cuda(ib.frame_numbers.detach().reshape(-1).to(torch.int32).contiguous(), "frame_numbers")
+    t = L.require_cuda(ib.sample_distances.detach().reshape(-1).float().contiguous(), "sample_distances")
+    ri = L.require_cuda(ib.ray_indices.detach().reshape(-1).to(torch.int64).contiguous(), "ray_indices")
+    return o, d, fr, t, ri
+
+
+def ray_offsets(ray_indices: torch.Tensor, num_rays: int) -> torch.Tensor:
+    off = torch.empty(num_rays + 1, dtype=torch.int32, device=ray_indices.device)
+    L.check(L.lib().hrf_ray_offsets(ray_indices.data_ptr(), ray_indices.shape[0], num_rays, off.data_ptr(), L.stream()))
+    return off
+
+
+@torch.no_grad()
+def prune_samples(input_batch: InputBatch, scene_representation: HumanRF, is_training: bool,
+                  render_step_size: float = 4e-4) -> None:
+    """volume_rendering.py:42-84.  Density-only pass + visibility mask (T>=1e-4 & alpha>=1e-4), in place."""
+    ib = input_batch
+    if is_training:
+        ib.sample_distances += torch.rand_like(ib.sample_distances) * render_step_size  # :63-64
+    nat = scene_representation.native()
+    o, d, fr, t, ri = _ray_arrays(ib)
+    n, num_rays = t.shape[0], ib.num_rays
+    dev = t.device
+    sigma, _, _, _ = nat.forward(nat.samples_rays(o, d, fr, t, ri), 0, want_geo=False, want_feat=False)
+    off = ray_offsets(ri, num_rays)
+    keep = torch.empty(n, dtype=torch.uint8, device=dev)
+    kept_off = torch.empty(num_rays + 1, dtype=torch.int32, device=dev)
+    out_t = torch.empty(n, dtype=torch.float32, device=dev)
+    out_ri = torch.empty(n, dtype=torch.int64, device=dev)
+    counter = torch.zeros(1, dtype=torch.int64, device=dev)
+    L.check(L.lib().hrf_prune(sigma.data_ptr(), t.data_ptr(), ri.data_ptr(), off.data_ptr(), num_rays,
+                              float(render_step_size), 1e-4, 1e-4, keep.data_ptr(), kept_off.data_ptr(),
+                              out_t.data_ptr(), out_ri.data_ptr(), counter.data_ptr(), L.stream()))
+    kept = int(counter.item())
+    ib.sample_distances = out_t[:kept].view(-1, 1)
+    ib.ray_indices = out_ri[:kept]
+
+
+class _RenderFunction(torch.autograd.Function):
+    """field forward (ray-batch form) + compositing; backward = composite bwd + fused field bwd."""
+
+    @staticmethod
+    def forward(ctx, model: HumanRF, o, d, fr, t, ri, num_rays, background, step, *params):
+        nat = model.native()
+        dev = t.device
+        needs_grad = any(ctx.needs_input_grad[9:])
+        samples = nat.samples_rays(o, d, fr, t, ri)
+        sigma, _, rgb, feat = nat.forward(samples, 1, want_geo=False, want_feat=needs_grad)
+        off = ray_offsets(ri, num_rays)
+        color = torch.empty((num_rays, 3), dtype=torch.float32, device=dev)
+        wsum = torch.empty((num_rays, 1), dtype=torch.float32, device=dev)
+        bg = None
+        if background is not None:
+            bg = torch.as_tensor(background, dtype=torch.float32, device=dev)
+            bg = bg.expand(num_rays, 3).contiguous() if bg.dim() < 2 or bg.shape[0] != num_rays else bg.contiguous()
+        L.check(L.lib().hrf_composite_forward(sigma.data_ptr(), rgb.data_ptr(), t.data_ptr(), off.data_ptr(), num_rays,
+                                              float(step), L.ptr(bg), color.data_ptr(), wsum.data_ptr(), None,
+                                              L.stream()))
+        ctx.model, ctx.num_rays, ctx.step = model, num_rays, float(step)
+        ctx.bg = bg
+        ctx.save_for_backward(o, d, fr, t, ri, sigma, rgb, off, feat if feat is not None else t)
+        return color, wsum
+
+    @staticmethod
+    def backward(ctx, d_color, d_wsum):
+        model = ctx.model
+        o, d, fr, t, ri, sigma, rgb, off, feat = ctx.saved_tensors
+        nat = model.native()
+        dev = t.device
+        n = t.shape[0]
+        dc = d_color.detach().float().contiguous() if d_color is not None else torch.zeros((ctx.num_rays, 3), device=dev)
+        dw = d_wsum.detach().float().reshape(-1).contiguous() if d_wsum is not None else None
+        d_sigma = torch.empty(n, dtype=torch.float32, device=dev)
+        d_rgb = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        L.check(L.lib().hrf_composite_backward(sigma.data_ptr(), rgb.data_ptr(), t.data_ptr(), off.data_ptr(),
+                                               ctx.num_rays, ctx.step, L.ptr(ctx.bg), dc.data_ptr(), L.ptr(dw),
+                                               d_sigma.data_ptr(), d_rgb.data_ptr(), L.stream()))
+        params = model.hot_parameters()
+        grads = [torch.zeros_like(p) for p in params]
+        nat.backward(nat.samples_rays(o, d, fr, t, ri), d_sigma, d_rgb, feat, grads)
+        return (None,) * 9 + tuple(grads)
+
+
+def render(input_batch: InputBatch, scene_representation: HumanRF, background_rgb: torch.Tensor, is_training: bool,
+           render_step_size: float = 4e-4) -> RenderOutput:
+    """volume_rendering.py:87-150.  color = sum w*rgb + background*(1 - sum w); weights_sum = sum w."""
+    ib = input_batch
+    o, d, fr, t, ri = _ray_arrays(ib)
+    color, wsum = _RenderFunction.apply(scene_representation, o, d, fr, t, ri, ib.num_rays, background_rgb,
+                                        render_step_size, *scene_representation.hot_parameters())
+    return RenderOutput(color=color, weights_sum=wsum)

@@ -1,0 +1,223 @@
+/*
+ * humanrf_b200 -- C ABI of the B200-native (sm_100a) HumanRF per-ray hot path.
+ *
+ * Drop-in boundary for the reference's three pybind11 torch extensions and the two
+ * third-party CUDA packages its hot path calls.  Every entry point
+ * takes plain DEVICE pointers (unless the name says host) + sizes + a CUDA stream handle
+ * (cudaStream_t passed as void*, NULL = legacy default stream); no torch types.  All
+ * functions return 0 on success and a non-zero code on failure; hrf_last_error() gives the
+ * message (the reference throws std::runtime_error from CHECK_CONTIGUITY_AND_DEVICE,
+ * actorshq/toolbox/native/utils.cuh:5-19; the Python host mirror raises RuntimeError).
+ * Launches are asynchronous on the given stream; nothing here synchronises except the
+ * functions documented as doing so.
+ */
+#ifndef HUMANRF_B200_H_
+#define HUMANRF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HRF_N_LEVELS 16        /* humanrf/args/model_args.py:26 n_levels            */
+#define HRF_N_FEATURES 32      /* n_levels * n_features_per_level (2)               */
+#define HRF_MLP_WIDTH 64       /* model_args.py:12 n_neurons                        */
+#define HRF_GEO_DIM 15         /* model_args.py:10 geometry_feature_dim             */
+#define HRF_MLP_BLOB_BYTES 20480 /* packed bf16 weights: sigma 64x32,16x64; colour 64x32,64x64,16x64 */
+
+const char* hrf_last_error(void);
+int hrf_version(void);
+/* device properties the host mirror needs: out[0]=SM count, out[1]=cc major, out[2]=cc minor */
+int hrf_device_info(int* out3);
+
+/* ------------------------------------------------------------------------------------------
+ * Occupancy grid ring.  Replaces occupancy_grid_native.OccupanyGrid
+ * (actorshq/dataset/native/occupancy_grid.cu:8-95): a ring of `buffer_size` G^3 occupancy
+ * volumes; add_grid copies a uint8 [G][G][G] (z,y,x) device tensor into the next slot and
+ * returns an int64 handle the sampler understands (the reference returns a
+ * cudaTextureObject_t; here it is the device address of a bit-packed G^3 volume).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct hrf_occgrid hrf_occgrid;
+int hrf_occgrid_create(uint64_t grid_resolution, int buffer_size, hrf_occgrid** out);
+int hrf_occgrid_destroy(hrf_occgrid* g);
+int hrf_occgrid_add(hrf_occgrid* g, const uint8_t* grid_u8, uint64_t res0, uint64_t res1, uint64_t res2,
+                    void* stream, int64_t* handle_out);
+/* test hook: evaluates the emulated `tex3D(handle, p) > 0` for n points (xyz normalised) */
+int hrf_occgrid_lookup(int64_t handle, int grid_resolution, const float* points_xyz, int64_t n,
+                       uint8_t* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Ray sampler.  Replaces ray_sampler_native.get_{rays,samples}_{aabb,occupancy}_minmax
+ * (actorshq/dataset/native/ray_sampler.cu:196-325).  Three phases, no host round trip inside:
+ *   hrf_sampler_rays   : compute_minmax_kernel (:80-147) for all R candidate rays, ray mask
+ *                        (optionally AND NOT light_mask, :254-257), device-side compaction,
+ *                        per-ray gathers (:258-266) and per-ray sample counts/offsets
+ *                        (:283-290, occupancy filter of :183-189 already applied).
+ *                        counters[0]=R' (kept rays), counters[1]=N' (kept samples).
+ *   hrf_sampler_samples: compute_sample_distances_kernel (:149-194) + final compaction
+ *                        (:322-323) written directly at the scanned offsets.
+ * rgba_pool / light_mask are DEVICE-resident pools here (the reference indexes a CPU pool and
+ * bounces through the host, :262); the Python mirror keeps the CPU-pool call signature.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  const int32_t* frame_numbers;      /* [B] */
+  const int32_t* camera_numbers;     /* [B] */
+  const int64_t* grid_handles;       /* [B] from hrf_occgrid_add (unused for aabb mode) */
+  const uint8_t* landscape_modes;    /* [B] bool */
+  const float*   inverse_krs;        /* [B,3,3], stored transposed as the reference does (data_loader.py:194-207) */
+  const float*   camera_origins;     /* [B,3] */
+  const float*   aabb;               /* [2,3] */
+  const uint8_t* rgba_pool;          /* [P,4] uint8 or NULL */
+  const uint8_t* light_mask;         /* [P] bool, indexed by pool pixel, or NULL */
+  const uint8_t* light_mask_rays;    /* [R] bool, indexed by candidate ray (host-pool callers), or NULL */
+  int32_t grid_resolution, image_width, image_height;
+  float step;
+  int32_t occupancy;                 /* 1: occupancy minmax + filter, 0: aabb only */
+  int32_t filter_light_bloom;
+  int32_t want_samples;              /* 0: get_rays_* variants (counts are all zero) */
+} hrf_sampler_params;
+
+int hrf_sampler_rays(const hrf_sampler_params* p, const int64_t* all_ray_indices, int64_t num_rays,
+                     /* full-size outputs [R] */
+                     uint8_t* ray_mask,
+                     /* compacted outputs, capacity R */
+                     float* ray_origins, float* ray_directions, float* rgba, int32_t* frame_numbers,
+                     int32_t* camera_numbers, float* minmaxes, int64_t* kept_ray_indices,
+                     int32_t* sample_offsets /* [R+1] exclusive scan of kept-sample counts */,
+                     int64_t* counters /* [2] device */, void* workspace, int64_t workspace_bytes, void* stream);
+int64_t hrf_sampler_workspace_bytes(int64_t num_rays);
+int hrf_sampler_samples(const hrf_sampler_params* p, int64_t num_kept_rays, const int64_t* kept_ray_indices,
+                        const float* ray_origins, const float* ray_directions, const float* minmaxes,
+                        const int32_t* sample_offsets, float* distances /* [N'] */,
+                        int32_t* relative_ray_indices /* [N'] */, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Radiance field.  Replaces HumanRF.density / HumanRF.forward
+ * (humanrf/scene_representation/humanrf.py:158-208): 4 tcnn HashGrids per segment
+ * (decomposition4d.py:79-129), compose_tensors (tensor_composition.cu:9-55), sigma MLP +
+ * truncated_exp (humanrf.py:181-186), SH/identity colour MLP (:188-206) in ONE kernel.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  const uint32_t* grid[4];           /* bf16x2 entries: xyz, xyt, yzt, xzt encodings     */
+  const float*    vectors;           /* [4, vec_res, 32] fp32 (decomposition4d.py:76-78) */
+  uint32_t level_offset[HRF_N_LEVELS]; /* entry offset of each level                      */
+  uint32_t level_size[HRF_N_LEVELS];   /* hashmap_size of each level (entries)            */
+  uint32_t hashed_mask;              /* bit l: level l uses the spatial hash             */
+  uint32_t n_entries;                /* entries per grid                                 */
+} hrf_segment;
+
+typedef struct {
+  const hrf_segment* segments;       /* device array [num_segments]                      */
+  const int32_t* frame_to_segment;   /* device [lut_size]   (humanrf.py:99)              */
+  const float*   frame_to_tlocal;    /* device [lut_size]   (humanrf.py:100-103)         */
+  const void*    mlp_blob;           /* device, HRF_MLP_BLOB_BYTES, see hrf_pack_layout   */
+  float    level_scale[HRF_N_LEVELS];
+  uint32_t level_res[HRF_N_LEVELS];
+  int32_t  num_segments, lut_size, vec_res;
+  float    density_scale;
+} hrf_field;
+
+/* Sample source: either explicit per-sample queries (QueryInput, query_io.py:6-13) or the
+ * ray-batch form used by prune_samples/render (volume_rendering.py:66-72,110-119). */
+typedef struct {
+  /* query form (ray_origins == NULL) */
+  const float* positions;            /* [N,3] in [-0.5,0.5] */
+  const float* directions;           /* [N,3] or NULL for density-only */
+  const int32_t* frame_numbers;      /* [N] */
+  /* ray-batch form */
+  const float* ray_origins;          /* [R,3] */
+  const float* ray_directions;       /* [R,3] */
+  const int32_t* ray_frame_numbers;  /* [R] */
+  const float* sample_distances;     /* [N] */
+  const int64_t* ray_indices;        /* [N] sorted ascending */
+  int64_t num_samples;
+} hrf_samples;
+
+/* mode: 0 = density only (sigma, geo), 1 = density + radiance.  Any output may be NULL.
+ * mlp_impl: 0 = tcgen05 tensor-core path (the product); 1 = SIMT fp32 debug path used only by
+ * tests to localise tensor-core descriptor faults. */
+int hrf_field_forward(const hrf_field* f, const hrf_samples* s, int mode, int mlp_impl,
+                      float* sigma /* [N] */, void* geo_bf16 /* [N,16] (col 0 = raw h0) */,
+                      float* rgb /* [N,3] */, void* feat_bf16 /* [N,32] composed features saved for backward, or NULL */,
+                      void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Compositing.  Replaces nerfacc.render_visibility / render_weight_from_density /
+ * accumulate_along_rays as called from humanrf/volume_rendering.py:75-84,123-145.
+ * ---------------------------------------------------------------------------------------- */
+/* ray_offsets[r] = first sample of ray r in the sorted ray_indices; ray_offsets[R] = N */
+int hrf_ray_offsets(const int64_t* ray_indices, int64_t num_samples, int64_t num_rays,
+                    int32_t* ray_offsets /* [R+1] */, void* stream);
+/* prune: keep_i = (T_i >= 1e-4) & (alpha_i >= 1e-4), alpha = 1-exp(-sigma*step); writes the
+ * kept samples compacted; counters[0] = kept count.  kept_offsets [R+1] workspace. */
+int hrf_prune(const float* sigma, const float* sample_distances, const int64_t* ray_indices,
+              const int32_t* ray_offsets, int64_t num_rays, float step, float early_stop_eps, float alpha_thre,
+              uint8_t* keep_mask /* [N] or NULL */, int32_t* kept_offsets /* [R+1] */,
+              float* out_distances, int64_t* out_ray_indices, int64_t* counters, void* stream);
+/* render: w_i = exp(-sum_{j<i} sigma_j*dt_j) * (1-exp(-sigma_i*dt_i)), dt=(t+step)-t;
+ * color = sum w*rgb (+ background*(1-sum w)), weights_sum = sum w. background: [R,3] or NULL. */
+int hrf_composite_forward(const float* sigma, const float* rgb, const float* sample_distances,
+                          const int32_t* ray_offsets, int64_t num_rays, float step, const float* background,
+                          float* color /* [R,3] */, float* weights_sum /* [R] */,
+                          float* weights /* [N] or NULL */, void* stream);
+/* backward of the above w.r.t. sigma and rgb given d_color [R,3], d_weights_sum [R] */
+int hrf_composite_backward(const float* sigma, const float* rgb, const float* sample_distances,
+                           const int32_t* ray_offsets, int64_t num_rays, float step, const float* background,
+                           const float* d_color, const float* d_weights_sum,
+                           float* d_sigma /* [N] */, float* d_rgb /* [N,3] */, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Backward of the radiance field (autograd of humanrf.py:158-208): recomputes the forward per
+ * 128-sample tile, runs MLP dgrad/wgrad on the tensor cores, scatters table / vector gradients.
+ * Gradients are ACCUMULATED (+=) into the fp32 buffers; the caller zeroes them.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+  float* grid[4];                    /* [n_entries,2] fp32, same order as hrf_segment.grid */
+  float* vectors;                    /* [4, vec_res, 32] fp32 */
+} hrf_segment_grads;
+
+int hrf_field_backward(const hrf_field* f, const hrf_samples* s, const hrf_segment_grads* seg_grads /* device array */,
+                       const float* d_sigma /* [N] */, const float* d_rgb /* [N,3] or NULL */,
+                       const void* feat_bf16 /* [N,32] from hrf_field_forward, or NULL to re-encode */,
+                       float* d_mlp /* fp32 [10240]: sigma W1,W2, colour W1,W2,W3 row-major [out,in] */,
+                       void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * tensor_composition_native parity (tensor_composition.cu:120-219): stand-alone fwd/bwd of
+ * sum_k feat3D_k * lerp(vector_k, coord_k) on fp16 features, as the reference's extension.
+ * ---------------------------------------------------------------------------------------- */
+int hrf_compose_tensors_forward(const void* xyz, const void* xyt, const void* yzt, const void* xzt /* half [N,F] */,
+                                const float* vectors /* [4,VR,F] */, const float* coords /* [N,4] */,
+                                int64_t n, int feature_dim, int vec_res, void* out /* half [N,F] */, void* stream);
+int hrf_compose_tensors_backward(const void* xyz, const void* xyt, const void* yzt, const void* xzt,
+                                 const float* vectors, const float* coords, const void* d_out, int64_t n,
+                                 int feature_dim, int vec_res, void* d_xyz, void* d_xyt, void* d_yzt, void* d_xzt,
+                                 float* d_vectors /* zero-initialised by the callee */, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimiser: fused Adam (run.py:101-104: betas (0.9,0.99), eps 1e-15) over a flat fp32 buffer,
+ * optionally refreshing the bf16 shadow copy the forward reads.  grad_scale multiplies the
+ * gradient first (1/global_ray_count for data-parallel means).
+ * ---------------------------------------------------------------------------------------- */
+int hrf_adam_step(float* param, float* exp_avg, float* exp_avg_sq, const float* grad, void* shadow_bf16 /* or NULL */,
+                  int64_t n, float lr, float beta1, float beta2, float eps, int step, float grad_scale,
+                  void* stream);
+int hrf_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Self tests (used by tests/ only): one 128xN x K tcgen05 MMA with caller-chosen descriptor
+ * fields, to pin the shared-memory descriptor encoding on real hardware.
+ * ---------------------------------------------------------------------------------------- */
+int hrf_selftest_umma(const void* a_bf16 /* [M,K] row-major */, const void* b_bf16 /* [N,K] row-major */,
+                      float* d /* [M,N] */, int m /* 64 or 128 */, int n, int k,
+                      /* physical placement of the 8x8 core matrices in shared memory (bytes) */
+                      uint32_t a_kstride, uint32_t a_mstride, uint32_t b_kstride, uint32_t b_nstride,
+                      /* descriptor fields (bytes) */
+                      uint32_t a_lbo, uint32_t a_sbo, uint32_t b_lbo, uint32_t b_sbo,
+                      int mn_major /* 1: both operands MN-major */, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HUMANRF_B200_H_ */
