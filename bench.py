@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the HumanRF per-ray hot path on B200 (see DESIGN.md "Measurement").
+
+A step = one pass of the hot path over one synthetic batch (SURVEY 8d / BASELINE.md section 2):
+4096 rays x 512 samples = 2,097,152 samples, segment_sizes=(50,) (log2T=18), 8 distinct frames of 15..64:
+    --mode render (default): fused field forward (4 hash grids x 16 levels -> compose -> sigma MLP -> colour MLP
+                             on tcgen05) + per-ray compositing  ->  4096 ray colours          [rays/s]
+    --mode train           : render forward + loss + fused backward + fused Adam               [rays/s]
+`value` is timed with CUDA events per step (inputs resident in HBM, L2 flushed between steps); `e2e`
+goes through the public API (humanrf_b200.volume_rendering.render) with pinned HOST buffers, H2D and D2H
+inside the timed region.  `--impl reference` times the CPU oracle port of the same path (the reference's
+tcnn/nerfacc path is CUDA-only and not installable here) on the box's host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+RAYS, SPR = 4096, 512
+SEGMENTS = (50,)
+ALG_BYTES_FWD = 3084          # 2048 B table gathers + 1024 B vector taps + 12 B stream, per sample
+METRIC = {"render": "render_rays_per_s", "train": "train_rays_per_s"}
+
+
+def dist_info():
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    return rank, world, local
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_workload(device, seed):
+    from humanrf_b200.synthetic import make_model, synthetic_rays
+
+    model, frames = make_model(SEGMENTS, seed=123, device=device)
+    batch = synthetic_rays(RAYS, SPR, frames, seed=seed)
+    return model, frames, batch
+
+
+def cpu_oracle_rate(sample_rays=64, repeats=1, threads=None):
+    """Reference arm / cpu_baseline: oracle encode+MLP+composite on a bounded sub-batch, rays/s."""
+    from humanrf_b200.synthetic import synthetic_rays
+    from oracle import field as ofield
+    from oracle import rendering as orender
+
+    threads = threads or os.cpu_count()
+    torch.set_num_threads(threads)
+    frames = tuple(range(15, 15 + sum(SEGMENTS)))
+    om = ofield.make_model(SEGMENTS, frames, seed=123, table_init="trained", bf16=False)
+    b = synthetic_rays(sample_rays, SPR, frames, seed=7)
+    pos = b["o"][b["ri"]] + b["t"].unsqueeze(1) * b["d"][b["ri"]]
+    best = None
+    with torch.no_grad():
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            sig, _, rgb = om.forward(pos, b["d"][b["ri"]], b["frames"][b["ri"]])
+            orender.render(b["t"], sig, rgb, b["ri"], sample_rays, None)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    return sample_rays / best, threads, f"{sample_rays} rays x {SPR} samples of the same workload, fp32, best of {repeats}"
+
+
+def run_reference(args):
+    rank, world, _ = dist_info()
+    if rank != 0:
+        return
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, cores, sample = cpu_oracle_rate(sample_rays=16, repeats=1)
+        if i >= args.warmup:
+            vals.append(v)
+    value = len(vals) / sum(1.0 / v for v in vals)
+    line = {"impl": "reference", "metric": METRIC[args.mode], "value": value, "unit": "rays/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * RAYS / value, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{RAYS} rays x {SPR} samples, segment_sizes={SEGMENTS}, render forward", "note":
+                       "CPU oracle port of the reference path (tcnn/nerfacc are CUDA-only and not installable offline)"},
+            "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="render", choices=["render", "train"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank, world, local = dist_info()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback (use --impl reference for the CPU oracle)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    import torch.distributed as dist
+
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from humanrf_b200 import _lib as L
+    from humanrf_b200.volume_rendering import ray_offsets, render
+
+    L.lib()
+    model, frames, b = build_workload(dev, seed=123 + rank)
+    if args.mode == "train":
+        from humanrf_b200.training import FusedTrainer
+
+        trainer = FusedTrainer(model, lr=1e-2, world_size=world)
+    nat = model.native()
+    g = {k: v.to(dev).contiguous() for k, v in b.items() if k in ("o", "d", "frames", "t", "ri", "rgba")}
+    n = g["t"].shape[0]
+    bg = torch.rand(RAYS, 3, device=dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    samples = nat.samples_rays(g["o"], g["d"], g["frames"], g["t"], g["ri"])
+    sigma = torch.empty(n, device=dev)
+    rgb = torch.empty(n, 3, device=dev)
+    color = torch.empty(RAYS, 3, device=dev)
+    wsum = torch.empty(RAYS, device=dev)
+    import ctypes as C
+
+    lib = L.lib()
+    launches = {"n": 0}
+
+    def step_render(ev=None):
+        L.check(lib.hrf_field_forward(C.byref(nat.field), C.byref(samples), 1, 0, sigma.data_ptr(), None, rgb.data_ptr(),
+                                      None, L.stream()))
+        if ev is not None:
+            ev.record()
+        off = ray_offsets(g["ri"], RAYS)
+        L.check(lib.hrf_composite_forward(sigma.data_ptr(), rgb.data_ptr(), g["t"].data_ptr(), off.data_ptr(), RAYS, 4e-4,
+                                          bg.data_ptr(), color.data_ptr(), wsum.data_ptr(), None, L.stream()))
+        launches["n"] += 3
+
+    def step_train(ev=None):
+        launches["n"] += trainer.step(g["o"], g["d"], g["frames"], g["t"], g["ri"], g["rgba"], RAYS, kernel_event=ev)
+
+    step = step_render if args.mode == "render" else step_train
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        step()
+    barrier()
+    clocks = ClockSampler(local)
+    launches["n"] = 0
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    t_wall = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()
+        ev[i][0].record()
+        step(ev[i][1])
+        ev[i][2].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    clk = clocks.stop()
+    step_ms = sum(e[0].elapsed_time(e[2]) for e in ev)
+    kern_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
+    tt = torch.tensor([step_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms = float(tt.item())
+    gpu_launches = launches["n"]
+
+    # ---- e2e through the public API with pinned host buffers -------------------------------------
+    host = {k: b[k].contiguous().pin_memory() for k in ("o", "d", "frames", "t", "ri", "rgba")}
+    host_color = torch.empty(RAYS, 3).pin_memory()
+    h2d = sum(host[k].numel() * host[k].element_size() for k in ("o", "d", "frames", "t", "ri"))
+    d2h = host_color.numel() * 4
+
+    from humanrf_b200.dataset.input_batch import InputBatch
+
+    def e2e_step():
+        bb = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        if args.mode == "render":
+            ib = InputBatch(ray_origins=bb["o"], ray_directions=bb["d"], frame_numbers=bb["frames"].view(-1, 1),
+                            sample_distances=bb["t"].view(-1, 1), ray_indices=bb["ri"], rgba=bb["rgba"])
+            with torch.no_grad():
+                out = render(ib, model, bg, is_training=False)
+            host_color.copy_(out.color, non_blocking=True)
+        else:
+            loss = trainer.step(bb["o"], bb["d"], bb["frames"], bb["t"], bb["ri"], bb["rgba"], RAYS, return_loss=True)
+            host_color[0, 0] = float(loss)  # the D2H read of the step's result
+        torch.cuda.synchronize()
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    k_e2e = max(3, args.steps // 2)
+    for _ in range(k_e2e):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = world * RAYS * k_e2e / float(te.item())
+    if args.mode == "train":
+        h2d += host["rgba"].numel() * 4
+        d2h = 4
+
+    if rank == 0:
+        value = world * RAYS * args.steps / (total_ms * 1e-3)
+        peak, which = load_peaks()
+        alg_bytes = ALG_BYTES_FWD * n if args.mode == "render" else 12300 * n
+        achieved = alg_bytes / (kern_ms * 1e-3) / 1e9 if args.mode == "render" else alg_bytes / (total_ms / args.steps * 1e-3) / 1e9
+        line = {
+            "metric": METRIC[args.mode], "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"{RAYS} rays x {SPR} samples/ray = {n} samples per GPU, segment_sizes={SEGMENTS} (log2T=18), "
+                                   f"8 frames of 15..64, {'forward render' if args.mode == 'render' else 'fwd+bwd+Adam'}",
+                       "mode": args.mode, "l2": "flushed between timed steps (256 MiB memset)", "parallelism": f"dp{world}",
+                       "samples_per_s": value * SPR},
+            "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "humanrf_b200.volume_rendering.render" if args.mode == "render" else "humanrf_b200.training.FusedTrainer.step"},
+            "gpu_launches": gpu_launches,
+            "clocks": clk,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": which, "kernel": "field_forward_kernel" if args.mode == "render" else "train step",
+                         "kernel_ms": kern_ms, "algorithmic_bytes_per_sample": ALG_BYTES_FWD if args.mode == "render" else 12300},
+            "wall_s_timed_loop": t_wall,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, cores, sample = cpu_oracle_rate(sample_rays=64, repeats=2)
+            line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -79,9 +79,8 @@ __global__ void compose_fwd_kernel(const __half* __restrict__ xyz, const __half*
   out[idx] = __float2half(r);
 }
 
-// Backward: thread = (sample, feature).  d_vectors: per-(axis,row,feature) fp32 atomics, but
-// first combined across the warp when neighbouring lanes hit the same row (match_any), which
-// removes most of the contention the reference has on the time axis.
+// Backward: thread = (sample, feature); d_vectors via fp32 atomics exactly like the reference
+// (tensor_composition.cu:109-111).  The fused training path (field_bwd.cu) does not use this kernel.
 __global__ void compose_bwd_kernel(const __half* __restrict__ xyz, const __half* __restrict__ xyt,
                                    const __half* __restrict__ yzt, const __half* __restrict__ xzt,
                                    const float* __restrict__ vec, const float* __restrict__ coords,
@@ -150,7 +149,7 @@ __global__ void __launch_bounds__(128, 1) selftest_umma_kernel(const SelfTestArg
   for (int e = tid; e < t.m * t.k; e += blockDim.x) {
     const int r = e / t.k, k = e % t.k;
     uint32_t off;
-    if (!t.mn_major)
+    if (!(t.mn_major & 1))
       off = (uint32_t)(k >> 3) * t.a_kstride + (uint32_t)(r >> 3) * t.a_mstride + (uint32_t)(r & 7) * 16u + (uint32_t)(k & 7) * 2u;
     else
       off = (uint32_t)(r >> 3) * t.a_mstride + (uint32_t)(k >> 3) * t.a_kstride + (uint32_t)(k & 7) * 16u + (uint32_t)(r & 7) * 2u;
@@ -159,7 +158,7 @@ __global__ void __launch_bounds__(128, 1) selftest_umma_kernel(const SelfTestArg
   for (int e = tid; e < t.n * t.k; e += blockDim.x) {
     const int r = e / t.k, k = e % t.k;
     uint32_t off;
-    if (!t.mn_major)
+    if (!(t.mn_major & 2))
       off = (uint32_t)(k >> 3) * t.b_kstride + (uint32_t)(r >> 3) * t.b_nstride + (uint32_t)(r & 7) * 16u + (uint32_t)(k & 7) * 2u;
     else
       off = (uint32_t)(r >> 3) * t.b_nstride + (uint32_t)(k >> 3) * t.b_kstride + (uint32_t)(k & 7) * 16u + (uint32_t)(r & 7) * 2u;
@@ -170,7 +169,7 @@ __global__ void __launch_bounds__(128, 1) selftest_umma_kernel(const SelfTestArg
   __syncthreads();
   tc_fence_after();
   if (tid == 0) {
-    const uint32_t idesc = make_idesc_bf16(t.m, t.n, t.mn_major, t.mn_major);
+    const uint32_t idesc = make_idesc_bf16(t.m, t.n, t.mn_major & 1, (t.mn_major >> 1) & 1);
     for (int k = 0; k < t.k / 16; ++k) {
       const uint64_t ad = make_smem_desc(smem_u32(sa) + (uint32_t)k * 2u * t.a_kstride, t.a_lbo, t.a_sbo);
       const uint64_t bd = make_smem_desc(smem_u32(sb) + (uint32_t)k * 2u * t.b_kstride, t.b_lbo, t.b_sbo);

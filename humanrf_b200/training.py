@@ -1,0 +1,159 @@
+"""Native training step for the HumanRF hot path (the fast path behind bench.py --mode train and the
+data-parallel driver).  Same maths as the reference's Trainer.train_step (humanrf/trainer.py:229-255:
+random background, Huber(delta=0.01) + 1e-3 * BCE, Adam lr 1e-2 betas (0.9,0.99) eps 1e-15,
+lr * lr_decay^(min(step/max,1)), run.py:101-104), but:
+
+* gradients are written by the fused backward kernel straight into ONE flat fp32 bucket (no per-parameter
+  zero-filled tensors, no autograd graph), which is also the single NCCL all-reduce message under data
+  parallelism;
+* Adam is one fused kernel per parameter that also refreshes the bf16 shadow table the forward reads;
+* bf16 needs no GradScaler, so the inf-check host sync of trainer.py:250-252 disappears.
+
+The autograd-compatible route (humanrf_b200.volume_rendering.render + torch.optim.Adam) stays available for
+running the reference's trainer.py unchanged.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .scene_representation.humanrf import HumanRF
+from .volume_rendering import ray_offsets
+
+
+class FusedTrainer:
+    def __init__(self, model: HumanRF, lr: float = 1e-2, betas=(0.9, 0.99), eps: float = 1e-15, lr_decay: float = 0.5,
+                 max_steps: int = 50001, bce_loss_weight: float = 1e-3, huber_delta: float = 0.01,
+                 render_step_size: float = 4e-4, world_size: int = 1, process_group=None, prune: bool = True,
+                 seed: int = 123):
+        self.model, self.lr, self.betas, self.eps = model, lr, betas, eps
+        self.lr_decay, self.max_steps = lr_decay, max_steps
+        self.bce_w, self.delta, self.step_size = bce_loss_weight, huber_delta, render_step_size
+        self.world, self.pg, self.prune = world_size, process_group, prune
+        self.params: List[torch.nn.Parameter] = model.hot_parameters()
+        dev = self.params[0].device
+        sizes = [p.numel() for p in self.params]
+        self.offsets = np.concatenate(([0], np.cumsum(sizes))).tolist()
+        total = self.offsets[-1]
+        self.grad = torch.zeros(total, dtype=torch.float32, device=dev)       # the all-reduce bucket
+        self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.grad_views = [self.grad[a:b] for a, b in zip(self.offsets[:-1], self.offsets[1:])]
+        self.t = 0
+        self.gen = torch.Generator(device=dev).manual_seed(seed)
+        self.nat = model.native()
+        m = model
+        sg = (L.SegmentGrads * m.num_segments)()
+        i = 0
+        for s in range(m.num_segments):
+            for k in range(4):
+                sg[s].grid[k] = self.grad_views[i].data_ptr()
+                i += 1
+            sg[s].vectors = self.grad_views[i].data_ptr()
+            i += 1
+        self.sg_dev = torch.from_numpy(np.frombuffer(bytes(sg), dtype=np.uint8).copy()).to(dev)
+        self.mlp_grad = self.grad[self.offsets[i]:]            # sigma params then colour params: contiguous 10240
+        assert self.mlp_grad.numel() == L.MLP_GRAD_ELEMS
+        self.last = {}
+
+    # ----------------------------------------------------------------------------------------------
+    def current_lr(self) -> float:
+        return self.lr * self.lr_decay ** min(self.t / self.max_steps, 1.0)  # run.py:102-104
+
+    def step(self, o, d, frames, t, ri, rgba, num_rays: int, kernel_event=None, return_loss: bool = False):
+        """One optimisation step on a ray batch given in InputBatch layout (device tensors).
+        Returns the number of kernels launched, or the loss value when return_loss."""
+        lib, nat, dev = L.lib(), self.model.native(), t.device
+        launches = 0
+        step = self.step_size
+        t = t.reshape(-1)
+        # ---- prune_samples (volume_rendering.py:42-84): jitter, density-only pass, visibility compaction
+        if self.prune:
+            t = t + torch.rand(t.shape, device=dev, generator=self.gen) * step
+            n0 = t.shape[0]
+            sigma0, _, _, _ = nat.forward(nat.samples_rays(o, d, frames, t, ri), 0, want_geo=False, want_feat=False)
+            off0 = ray_offsets(ri, num_rays)
+            keep = torch.empty(n0, dtype=torch.uint8, device=dev)
+            kept_off = torch.empty(num_rays + 1, dtype=torch.int32, device=dev)
+            t2 = torch.empty(n0, dtype=torch.float32, device=dev)
+            ri2 = torch.empty(n0, dtype=torch.int64, device=dev)
+            counter = torch.zeros(1, dtype=torch.int64, device=dev)
+            L.check(lib.hrf_prune(sigma0.data_ptr(), t.data_ptr(), ri.data_ptr(), off0.data_ptr(), num_rays, step, 1e-4,
+                                  1e-4, keep.data_ptr(), kept_off.data_ptr(), t2.data_ptr(), ri2.data_ptr(),
+                                  counter.data_ptr(), L.stream()))
+            kept = int(counter.item())
+            t, ri = t2[:kept], ri2[:kept]
+            launches += 7
+        n = t.shape[0]
+        # ---- forward: fused field + compositing
+        samples = nat.samples_rays(o, d, frames, t, ri)
+        sigma, _, rgb, feat = nat.forward(samples, 1, want_geo=False, want_feat=True)
+        if kernel_event is not None:
+            kernel_event.record()
+        off = ray_offsets(ri, num_rays)
+        bg = torch.rand((num_rays, 3), device=dev, generator=self.gen)           # trainer.py:237
+        color = torch.empty((num_rays, 3), dtype=torch.float32, device=dev)
+        wsum = torch.empty((num_rays, 1), dtype=torch.float32, device=dev)
+        L.check(lib.hrf_composite_forward(sigma.data_ptr(), rgb.data_ptr(), t.data_ptr(), off.data_ptr(), num_rays, step,
+                                          bg.data_ptr(), color.data_ptr(), wsum.data_ptr(), None, L.stream()))
+        # ---- loss on the [R,3] outputs (tiny): Huber + BCE, gradients by autograd on the leaf outputs
+        color.requires_grad_(True)
+        wsum.requires_grad_(True)
+        mask = rgba[:, 3:4]
+        gt = rgba[:, :3] * mask + bg * (1 - mask)
+        photo = torch.nn.functional.huber_loss(color, gt, delta=self.delta, reduction="mean")
+        pc = torch.clamp(wsum, min=0, max=1)
+        bce = -(mask * torch.log(pc + 1e-10) + (1 - mask) * torch.log(1 - pc + 1e-10))
+        loss = photo + bce.mean() * self.bce_w
+        loss.backward()
+        # ---- backward: compositing, then the fused field backward into the flat bucket
+        d_sigma = torch.empty(n, dtype=torch.float32, device=dev)
+        d_rgb = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        L.check(lib.hrf_composite_backward(sigma.data_ptr(), rgb.data_ptr(), t.data_ptr(), off.data_ptr(), num_rays, step,
+                                           bg.data_ptr(), color.grad.data_ptr(), wsum.grad.reshape(-1).data_ptr(),
+                                           d_sigma.data_ptr(), d_rgb.data_ptr(), L.stream()))
+        self.grad.zero_()
+        L.check(lib.hrf_field_backward(C.byref(nat.field), C.byref(samples), self.sg_dev.data_ptr(), d_sigma.data_ptr(),
+                                       d_rgb.data_ptr(), feat.data_ptr(), self.mlp_grad.data_ptr(), L.stream()))
+        launches += 8 + 12
+        # ---- data parallel: one all-reduce of the flat bucket (sum), mean over ranks folded into Adam's grad_scale
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.pg)
+            launches += 1
+        self.apply_adam(1.0 / self.world)
+        launches += len(self.params) + 3
+        self.last = {"samples": n, "loss": loss.detach()}
+        if return_loss:
+            return float(loss.item())
+        return launches
+
+    def apply_adam(self, grad_scale: float) -> None:
+        lib, nat = L.lib(), self.nat
+        self.t += 1
+        lr = self.current_lr()
+        i = 0
+        with torch.no_grad():
+            for s, fg in enumerate(self.model.feature_grids):
+                for k in range(4):
+                    self._adam(i, nat.shadows[s][k], lr, grad_scale)
+                    i += 1
+                self._adam(i, None, lr, grad_scale)
+                i += 1
+            self._adam(i, None, lr, grad_scale)
+            self._adam(i + 1, None, lr, grad_scale)
+            m = self.model
+            flat = torch.cat((m.sigma_net.params.detach(), m.color_net.params.detach()))
+            nat.blob.copy_(flat[nat.perm].to(torch.bfloat16))
+
+    def _adam(self, i: int, shadow: Optional[torch.Tensor], lr: float, grad_scale: float) -> None:
+        p = self.params[i]
+        a, b = self.offsets[i], self.offsets[i + 1]
+        L.check(L.lib().hrf_adam_step(p.data_ptr(), self.exp_avg[a:b].data_ptr(), self.exp_avg_sq[a:b].data_ptr(),
+                                      self.grad[a:b].data_ptr(), L.ptr(shadow), b - a, lr, self.betas[0], self.betas[1],
+                                      self.eps, self.t, grad_scale, L.stream()))

@@ -215,7 +215,7 @@ int hrf_selftest_umma(const void* a_bf16 /* [M,K] row-major */, const void* b_bf
                       uint32_t a_kstride, uint32_t a_mstride, uint32_t b_kstride, uint32_t b_nstride,
                       /* descriptor fields (bytes) */
                       uint32_t a_lbo, uint32_t a_sbo, uint32_t b_lbo, uint32_t b_sbo,
-                      int mn_major /* 1: both operands MN-major */, void* stream);
+                      int mn_major /* bit 0: A is MN-major, bit 1: B is MN-major */, void* stream);
 
 #ifdef __cplusplus
 }

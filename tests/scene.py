@@ -1,0 +1,58 @@
+"""Synthetic ActorsHQ-like scene for the sampler tests and the bench: occupancy grid =
+union of 3 ellipsoids in [-0.5,0.5]^3, cameras on a ring at distance 2 looking at the origin."""
+from __future__ import annotations
+
+import numpy as np
+
+from humanrf_b200.dataset.cameras import inverse_kr, projection_matrix_world2pixel
+
+
+def ellipsoid_grid(G=128, seed=0):
+    rng = np.random.default_rng(seed)
+    c = (np.arange(G) + 0.5) / G - 0.5
+    z, y, x = np.meshgrid(c, c, c, indexing="ij")
+    occ = np.zeros((G, G, G), bool)
+    for _ in range(3):
+        ctr = rng.uniform(-0.15, 0.15, 3)
+        rad = rng.uniform(0.08, 0.25, 3)
+        occ |= ((x - ctr[0]) / rad[0]) ** 2 + ((y - ctr[1]) / rad[1]) ** 2 + ((z - ctr[2]) / rad[2]) ** 2 <= 1.0
+    return (occ * 255).astype(np.uint8)
+
+
+def look_at_camera(pos, width, height, f=1.773863):
+    """RDF camera at `pos` looking at the origin; returns (world2pixel 4x4, rotation axis-angle)."""
+    fwd = -pos / np.linalg.norm(pos)
+    up = np.array([0.0, -1.0, 0.0])
+    right = np.cross(fwd, up)
+    right /= np.linalg.norm(right)
+    down = np.cross(fwd, right)
+    Rm = np.stack([right, down, fwd], 1)  # camera->world
+    # axis-angle from rotation matrix
+    ang = np.arccos(np.clip((np.trace(Rm) - 1) / 2, -1, 1))
+    if ang < 1e-9:
+        aa = np.zeros(3)
+    else:
+        aa = ang / (2 * np.sin(ang)) * np.array([Rm[2, 1] - Rm[1, 2], Rm[0, 2] - Rm[2, 0], Rm[1, 0] - Rm[0, 1]])
+    return projection_matrix_world2pixel(width, height, aa, pos, np.array([f, f * width / height]), np.array([0.5, 0.5]))
+
+
+def make_scene(num_images=4, width=96, height=72, G=128, seed=0, portrait_every=3):
+    rng = np.random.default_rng(seed)
+    inv, org, land = [], [], []
+    for i in range(num_images):
+        a = 2 * np.pi * i / num_images + 0.3
+        pos = np.array([2.0 * np.cos(a), rng.uniform(-0.4, 0.4), 2.0 * np.sin(a)])
+        ls = not (portrait_every and i % portrait_every == portrait_every - 1)
+        w, h = (width, height) if ls else (height, width)
+        inv.append(inverse_kr(look_at_camera(pos, w, h)))
+        org.append(pos.astype(np.float32))
+        land.append(ls)
+    grids = [ellipsoid_grid(G, seed + i % 2) for i in range(num_images)]
+    P = num_images * width * height
+    return dict(
+        inverse_krs=np.stack(inv).astype(np.float32), camera_origins=np.stack(org).astype(np.float32),
+        landscape=np.array(land), grids=grids, G=G, width=width, height=height,
+        frame_numbers=(15 + np.arange(num_images) % 6).astype(np.int32),
+        camera_numbers=rng.integers(0, 160, num_images).astype(np.int32),
+        rgba=rng.integers(0, 256, (P, 4)).astype(np.uint8), light_mask=rng.random(P) < 0.05,
+        aabb=np.array([[-0.45, -0.5, -0.4], [0.5, 0.45, 0.5]], np.float32))

@@ -1,0 +1,103 @@
+"""Parity of the per-ray scan kernels (prune / weights / accumulate and their backward) with the oracle
+restating nerfacc 0.3.1 as called from volume_rendering.py:75-84,123-145."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import synthetic_rays
+from humanrf_b200 import _lib as L
+from humanrf_b200.volume_rendering import ray_offsets
+from oracle import rendering as R
+
+pytestmark = pytest.mark.gpu
+
+
+def _batch(num_rays, spr, seed=1, ragged=True, sigma_scale=400.0):
+    b = synthetic_rays(num_rays, spr, tuple(range(15, 21)), seed=seed, ragged=ragged)
+    g = torch.Generator().manual_seed(seed)
+    n = b["t"].shape[0]
+    sigma = torch.rand(n, generator=g) ** 4 * sigma_scale
+    sigma[torch.rand(n, generator=g) < 0.3] *= 1e-3      # plenty of alpha < 1e-4
+    rgb = torch.rand(n, 3, generator=g)
+    return b, sigma, rgb
+
+
+def test_ray_offsets_and_prune(cuda):
+    for seed, (nr, spr) in enumerate([(257, 70), (64, 513), (5, 3), (40, 0)]):
+        b, sigma, _ = _batch(nr, max(spr, 1), seed, ragged=spr != 513)
+        if spr == 0:
+            b["ri"], b["t"], sigma = b["ri"][:0], b["t"][:0], sigma[:0]
+        ri, t = b["ri"].to(cuda), b["t"].to(cuda)
+        off = ray_offsets(ri, nr)
+        exp_off = np.searchsorted(b["ri"].numpy(), np.arange(nr + 1))
+        np.testing.assert_array_equal(off.cpu().numpy(), exp_off)
+        n = t.shape[0]
+        keep = torch.empty(n, dtype=torch.uint8, device=cuda)
+        kept_off = torch.empty(nr + 1, dtype=torch.int32, device=cuda)
+        out_t = torch.empty(n, device=cuda)
+        out_ri = torch.empty(n, dtype=torch.int64, device=cuda)
+        counter = torch.zeros(1, dtype=torch.int64, device=cuda)
+        L.check(L.lib().hrf_prune(sigma.to(cuda).data_ptr(), t.data_ptr(), ri.data_ptr(), off.data_ptr(), nr, 4e-4, 1e-4,
+                                  1e-4, keep.data_ptr(), kept_off.data_ptr(), out_t.data_ptr(), out_ri.data_ptr(),
+                                  counter.data_ptr(), L.stream()))
+        exp = R.prune_mask(sigma, b["ri"]).numpy()
+        got = keep.bool().cpu().numpy()
+        # identical except where T or alpha sits within float rounding of the 1e-4 thresholds
+        alphas = 1.0 - torch.exp(-sigma.double() * 4e-4)
+        T = R._exclusive_by_ray((1.0 - alphas), b["ri"], "prod").numpy()
+        near = (np.abs(T - 1e-4) < 1e-8) | (np.abs(alphas.numpy() - 1e-4) < 1e-9)
+        assert (got != exp)[~near].sum() == 0, ((got != exp).sum(), near.sum())
+        k = int(counter.item())
+        assert k == got.sum()
+        np.testing.assert_array_equal(out_t[:k].cpu().numpy(), b["t"].numpy()[got])
+        np.testing.assert_array_equal(out_ri[:k].cpu().numpy(), b["ri"].numpy()[got])
+        np.testing.assert_array_equal(kept_off.cpu().numpy(), np.concatenate(([0], np.cumsum(np.bincount(b["ri"].numpy()[got], minlength=nr)))))
+
+
+@pytest.mark.parametrize("with_bg", [False, True])
+def test_composite_forward_backward(cuda, with_bg):
+    nr = 193
+    b, sigma, rgb = _batch(nr, 90, seed=7)
+    g = torch.Generator().manual_seed(3)
+    bg = torch.rand(nr, 3, generator=g) if with_bg else None
+    s64 = sigma.double().requires_grad_(True)
+    c64 = rgb.double().requires_grad_(True)
+    # oracle in float64 but with the float32 dt = (t+step)-t the reference feeds nerfacc
+    t32 = b["t"]
+    dt = ((t32 + 4e-4) - t32).double()
+    sdt = s64 * dt
+    T = torch.exp(-R._exclusive_by_ray(sdt, b["ri"], "sum"))
+    w = T * (1 - torch.exp(-sdt))
+    col = R.accumulate(w, b["ri"], c64, nr)
+    ws = R.accumulate(w, b["ri"], None, nr)
+    if with_bg:
+        col = col + bg.double() * (1 - ws)
+    dcol = torch.randn(nr, 3, generator=g).double()
+    dws = torch.randn(nr, 1, generator=g).double()
+    (col * dcol).sum().add((ws * dws).sum()).backward()
+
+    off = ray_offsets(b["ri"].to(cuda), nr)
+    sig_d, rgb_d, t_d = sigma.to(cuda), rgb.to(cuda).contiguous(), b["t"].to(cuda)
+    color = torch.empty(nr, 3, device=cuda)
+    wsum = torch.empty(nr, device=cuda)
+    wts = torch.empty(t_d.shape[0], device=cuda)
+    bg_d = bg.to(cuda).contiguous() if with_bg else None
+    lib = L.lib()
+    L.check(lib.hrf_composite_forward(sig_d.data_ptr(), rgb_d.data_ptr(), t_d.data_ptr(), off.data_ptr(), nr, 4e-4,
+                                      L.ptr(bg_d), color.data_ptr(), wsum.data_ptr(), wts.data_ptr(), L.stream()))
+    np.testing.assert_allclose(wts.cpu().numpy(), w.detach().numpy(), rtol=2e-4, atol=2e-7)
+    np.testing.assert_allclose(color.cpu().numpy(), col.detach().numpy(), rtol=2e-4, atol=2e-6)
+    np.testing.assert_allclose(wsum.cpu().numpy(), ws.detach().numpy()[:, 0], rtol=2e-4, atol=2e-6)
+    # fp32 oracle path used by the rest of the suite agrees too
+    c32, w32 = R.render(b["t"], sigma, rgb, b["ri"], nr, bg)
+    np.testing.assert_allclose(color.cpu().numpy(), c32.numpy(), rtol=1e-3, atol=1e-5)
+
+    d_sigma = torch.empty_like(sig_d)
+    d_rgb = torch.empty_like(rgb_d)
+    dc_d, dw_d = dcol.float().to(cuda).contiguous(), dws.float().reshape(-1).to(cuda).contiguous()
+    L.check(lib.hrf_composite_backward(sig_d.data_ptr(), rgb_d.data_ptr(), t_d.data_ptr(), off.data_ptr(), nr, 4e-4,
+                                       L.ptr(bg_d), dc_d.data_ptr(), dw_d.data_ptr(), d_sigma.data_ptr(),
+                                       d_rgb.data_ptr(), L.stream()))
+    gs, gc = s64.grad.numpy(), c64.grad.numpy()
+    np.testing.assert_allclose(d_rgb.cpu().numpy(), gc, rtol=3e-4, atol=1e-6)
+    np.testing.assert_allclose(d_sigma.cpu().numpy(), gs, rtol=2e-3, atol=2e-6 * np.abs(gs).max())
