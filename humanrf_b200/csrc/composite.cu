@@ -262,7 +262,7 @@ extern "C" int hrf_prune(const float* sigma, const float* sample_distances, cons
                          float alpha_thre, uint8_t* keep_mask, int32_t* kept_offsets, float* out_distances,
                          int64_t* out_ray_indices, int64_t* counters, void* stream) {
   (void)ray_indices;
-  HRF_REQUIRE(keep_mask != nullptr && kept_offsets != nullptr && counters != nullptr, "null workspace");
+  HRF_REQUIRE(kept_offsets != nullptr && counters != nullptr, "null workspace");  // keep_mask may be NULL only for N == 0
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (num_rays == 0) {
     HRF_CUDA(cudaMemsetAsync(counters, 0, sizeof(int64_t), st));

@@ -198,6 +198,7 @@ extern "C" int hrf_field_forward(const hrf_field* f, const hrf_samples* s, int m
   HRF_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (density) or 1 (density+radiance)");
   HRF_REQUIRE(s->num_samples >= 0, "negative sample count");
   HRF_REQUIRE(f->mlp_blob != nullptr && f->segments != nullptr, "field not initialised");
+  if (s->num_samples == 0) return 0;
   if (s->ray_origins != nullptr) {
     HRF_REQUIRE(s->ray_directions && s->ray_frame_numbers && s->sample_distances && s->ray_indices,
                 "ray-batch form needs origins, directions, frame numbers, distances and ray indices");

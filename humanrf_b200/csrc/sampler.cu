@@ -32,19 +32,23 @@ __device__ __forceinline__ int fix8(float p, float G) {
   const float xb = __fsub_rn(__fmul_rn(p, G), 0.5f);
   return (int)floorf(__fadd_rn(__fmul_rn(xb, 256.f), 0.5f));
 }
+// Per-corner weight of the hardware filter (fitted on a B200 texture unit, see oracle/sampler.py):
+// W = (((wx*wz + 128) >> 8) * wy + 128) >> 8 in 1/256 units; the sample is "> 0" iff an occupied
+// corner has W >= 1.
 __device__ __forceinline__ bool occ_lookup(const uint32_t* __restrict__ bits, int G, float x, float y, float z) {
   const float Gf = (float)G;
   const int qx = fix8(x, Gf), qy = fix8(y, Gf), qz = fix8(z, Gf);
   const int ix = qx >> 8, iy = qy >> 8, iz = qz >> 8;
-  const bool ax = (qx & 255) != 0, ay = (qy & 255) != 0, az = (qz & 255) != 0;
+  const int ax = qx & 255, ay = qy & 255, az = qz & 255;
   const int x0 = min(max(ix, 0), G - 1), x1 = min(max(ix + 1, 0), G - 1);
   const int y0 = min(max(iy, 0), G - 1), y1 = min(max(iy + 1, 0), G - 1);
   const int z0 = min(max(iz, 0), G - 1), z1 = min(max(iz + 1, 0), G - 1);
   bool occ = false;
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
-    const bool w = ((c & 1) ? ax : true) && ((c & 2) ? ay : true) && ((c & 4) ? az : true);
-    if (w) {
+    const int wx = (c & 1) ? ax : 256 - ax, wy = (c & 2) ? ay : 256 - ay, wz = (c & 4) ? az : 256 - az;
+    const int w = ((((wx * wz + 128) >> 8) * wy) + 128) >> 8;
+    if (w > 0) {
       const uint32_t bit = ((uint32_t)((c & 4) ? z1 : z0) * (uint32_t)G + (uint32_t)((c & 2) ? y1 : y0)) * (uint32_t)G +
                            (uint32_t)((c & 1) ? x1 : x0);
       occ |= (__ldg(bits + (bit >> 5)) >> (bit & 31u)) & 1u;

@@ -234,6 +234,7 @@ class _NativeField:
         s.directions = None if directions is None else directions.data_ptr()
         s.frame_numbers = frame_numbers.data_ptr()
         s.num_samples = positions.shape[0]
+        s._keep = (positions, directions, frame_numbers)   # the struct holds raw pointers: keep the tensors alive
         return s
 
     def samples_rays(self, ray_origins, ray_directions, ray_frames, distances, ray_indices) -> L.Samples:
@@ -244,6 +245,7 @@ class _NativeField:
         s.sample_distances = distances.data_ptr()
         s.ray_indices = ray_indices.data_ptr()
         s.num_samples = distances.shape[0]
+        s._keep = (ray_origins, ray_directions, ray_frames, distances, ray_indices)
         return s
 
     def forward(self, samples: L.Samples, mode: int, want_geo: bool, want_feat: bool, mlp_impl: int = 0):

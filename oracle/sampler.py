@@ -13,9 +13,9 @@ mismatch rate against a real build of the reference is measured on the GPU box
 
 Hardware trilinear filtering is emulated with the documented 1.8 fixed-point weights
 (CUDA Programming Guide, "Linear Filtering"): xB = x*G - 0.5, q = floor(xB*256 + 0.5),
-i = q >> 8, alpha = (q & 255)/256; a sample is "> 0" iff any corner with a non-zero weight
-holds a non-zero voxel.  Pinned against a real tex3D on the GPU box
-(tests/test_texture_probe_gpu.py).
+i = q >> 8, alpha = (q & 255)/256, plus the 8-bit result precision measured on a real B200
+texture unit (see tex_occupied).  Pinned against a real tex3D on the GPU box
+(tests/test_texture_probe_gpu.py), exact except at .5 rounding ties.
 """
 from __future__ import annotations
 
@@ -51,7 +51,13 @@ def _gmax(a, b):  # glm::max(a,b) = (a < b) ? b : a
 
 def tex_occupied(grid: np.ndarray, p: np.ndarray) -> np.ndarray:
     """grid: uint8 [G,G,G] indexed [z][y][x]; p: [N,3] float32 normalised coords (x,y,z).
-    Emulates tex3D<float>(...) > 0 for the reference's texture descriptor."""
+    Emulates tex3D<float>(...) > 0 for the reference's texture descriptor.
+
+    Model fitted to a real B200 texture unit (scripts/probe_texture.py): per-axis alpha in 1.8 fixed point,
+    rounded half-up; the filter result itself has 8 fractional bits; each corner weight is
+    W = (((wx*wz + 128) >> 8) * wy + 128) >> 8 with w = 256-alpha / alpha, and the result is > 0 iff an
+    occupied corner has W >= 1.  Residual disagreement with the hardware is confined to exact .5 ties of
+    those roundings (measured < 2e-4 on adversarial points, tests/test_texture_probe_gpu.py)."""
     G = grid.shape[0]
     q = np.floor(((p.astype(f32) * f32(G)).astype(f32) - f32(0.5)).astype(f32) * f32(256.0) + f32(0.5))
     q = q.astype(np.int64)
@@ -60,15 +66,16 @@ def tex_occupied(grid: np.ndarray, p: np.ndarray) -> np.ndarray:
     occ = np.zeros(p.shape[0], bool)
     gb = grid > 0
     for dz in (0, 1):
-        wz = (a[:, 2] > 0) if dz else np.ones(p.shape[0], bool)
+        wz = a[:, 2] if dz else 256 - a[:, 2]
         iz = np.clip(i0[:, 2] + dz, 0, G - 1)
         for dy in (0, 1):
-            wy = (a[:, 1] > 0) if dy else np.ones(p.shape[0], bool)
+            wy = a[:, 1] if dy else 256 - a[:, 1]
             iy = np.clip(i0[:, 1] + dy, 0, G - 1)
             for dx in (0, 1):
-                wx = (a[:, 0] > 0) if dx else np.ones(p.shape[0], bool)
+                wx = a[:, 0] if dx else 256 - a[:, 0]
                 ix = np.clip(i0[:, 0] + dx, 0, G - 1)
-                occ |= wz & wy & wx & gb[iz, iy, ix]
+                w = ((((wx * wz + 128) >> 8) * wy) + 128) >> 8
+                occ |= (w > 0) & gb[iz, iy, ix]
     return occ
 
 
