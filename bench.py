@@ -94,43 +94,26 @@ def build_workload(device, seed):
     return model, frames, batch
 
 
-def cpu_oracle_rate(sample_rays=64, repeats=1, threads=None):
-    """Reference arm / cpu_baseline: oracle encode+MLP+composite on a bounded sub-batch, rays/s."""
-    from humanrf_b200.synthetic import synthetic_rays
-    from oracle import field as ofield
-    from oracle import rendering as orender
-
-    threads = threads or os.cpu_count()
-    torch.set_num_threads(threads)
-    frames = tuple(range(15, 15 + sum(SEGMENTS)))
-    om = ofield.make_model(SEGMENTS, frames, seed=123, table_init="trained", bf16=False)
-    b = synthetic_rays(sample_rays, SPR, frames, seed=7)
-    pos = b["o"][b["ri"]] + b["t"].unsqueeze(1) * b["d"][b["ri"]]
-    best = None
-    with torch.no_grad():
-        for _ in range(repeats):
-            t0 = time.perf_counter()
-            sig, _, rgb = om.forward(pos, b["d"][b["ri"]], b["frames"][b["ri"]])
-            orender.render(b["t"], sig, rgb, b["ri"], sample_rays, None)
-            dt = time.perf_counter() - t0
-            best = dt if best is None else min(best, dt)
-    return sample_rays / best, threads, f"{sample_rays} rays x {SPR} samples of the same workload, fp32, best of {repeats}"
+def cpu_oracle_rate(steps=3, warmup=1, rays_per_worker=16):
+    """Reference arm / cpu_baseline: the CPU oracle port of encode+MLP+composite on a bounded sample of the same
+    workload, one single-threaded worker per host core (oracle/cpu_bench.py, run in a fresh process)."""
+    cmd = [sys.executable, str(ROOT / "oracle" / "cpu_bench.py"), "--steps", str(steps), "--warmup", str(warmup),
+           "--rays-per-worker", str(rays_per_worker), "--samples-per-ray", str(SPR), "--segments", *map(str, SEGMENTS)]
+    out = subprocess.run(cmd, capture_output=True, text=True, check=True).stdout.strip().splitlines()[-1]
+    r = json.loads(out)
+    return r["rays_per_s"], r["cores"], r["sample"], r
 
 
 def run_reference(args):
     rank, world, _ = dist_info()
     if rank != 0:
         return
-    vals = []
-    for i in range(args.warmup + args.steps):
-        v, cores, sample = cpu_oracle_rate(sample_rays=16, repeats=1)
-        if i >= args.warmup:
-            vals.append(v)
-    value = len(vals) / sum(1.0 / v for v in vals)
+    value, cores, sample, r = cpu_oracle_rate(steps=args.steps, warmup=args.warmup, rays_per_worker=4)
     line = {"impl": "reference", "metric": METRIC[args.mode], "value": value, "unit": "rays/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * RAYS / value, "higher_is_better": True,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{RAYS} rays x {SPR} samples, segment_sizes={SEGMENTS}, render forward", "note":
+            "config": {"workload": f"{RAYS} rays x {SPR} samples, segment_sizes={SEGMENTS}, render forward; each step = "
+                                   f"{r['rays_per_step']} rays of it", "note":
                        "CPU oracle port of the reference path (tcnn/nerfacc are CUDA-only and not installable offline)"},
             "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -287,7 +270,7 @@ def main():
             "wall_s_timed_loop": t_wall,
         }
         if world == 1 and not args.no_cpu_baseline:
-            v, cores, sample = cpu_oracle_rate(sample_rays=64, repeats=2)
+            v, cores, sample, _ = cpu_oracle_rate(steps=3, warmup=1, rays_per_worker=16)
             line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample}
         print(json.dumps(line))
     if world > 1:

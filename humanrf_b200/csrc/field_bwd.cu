@@ -44,7 +44,6 @@ struct BwdArgs {
   const float* d_rgb;
   const uint4* feat_in;  // bf16 [N,32] saved by the forward, or NULL (re-encode)
   float* d_mlp;
-  float* dbg;  // test hook: [N,64] intermediates, or NULL
 };
 
 // D[128,Nin] = G[128,Kout] * W[Kout,Nin]  : A = gradient tile (K-major), B = forward blob read MN-major
@@ -254,21 +253,9 @@ __global__ void __launch_bounds__(kTile, 2) field_backward_kernel(const __grid_c
     // ---------------- forward recompute ----------------
     mma_round(sm, phase, [&] { issue_layer(tm + kColWork, a_feat, wbase + kWSig1, 64, 32); });
     tmem_ld64(trow + kColWork, v);
-    if (args.dbg != nullptr && valid) {
-      const uint4 fr = *reinterpret_cast<const uint4*>(sm.feat + roff);
-      const uint4 wr = *reinterpret_cast<const uint4*>(sm.w);
-      const uint32_t fa[4] = {fr.x, fr.y, fr.z, fr.w}, wa[4] = {wr.x, wr.y, wr.z, wr.w};
-      for (int c = 0; c < 4; ++c) {
-        args.dbg[i * 64 + 32 + 2 * c] = bf16_lo(fa[c]), args.dbg[i * 64 + 33 + 2 * c] = bf16_hi(fa[c]);
-        args.dbg[i * 64 + 48 + 2 * c] = bf16_lo(wa[c]), args.dbg[i * 64 + 49 + 2 * c] = bf16_hi(wa[c]);
-      }
-      for (int c = 0; c < 8; ++c) args.dbg[i * 64 + 40 + c] = v[c];
-    }
     store_relu64(sm.hs, roff, v);
     mma_round(sm, phase, [&] { issue_layer(tm + kColWork, a_hs, wbase + kWSig2, 16, 64); });
     tmem_ld16(trow + kColWork, o);
-    if (args.dbg != nullptr && valid)
-      for (int c = 0; c < 8; ++c) args.dbg[i * 64 + 56 + c] = o[c];
     const float h0 = o[0];
     {
       float sh[16];
@@ -303,9 +290,6 @@ __global__ void __launch_bounds__(kTile, 2) field_backward_kernel(const __grid_c
           d3[c] = args.d_rgb[3 * i + c] * r * (1.f - r);
         }
       }
-      if (args.dbg != nullptr && valid) {
-        for (int c = 0; c < 3; ++c) args.dbg[i * 64 + 18 + c] = o[c], args.dbg[i * 64 + 21 + c] = d3[c];
-      }
       *reinterpret_cast<uint4*>(sm.g3 + 0 * kAChunk + roff) =
           make_uint4(pack_bf16x2(d3[0], d3[1]), pack_bf16x2(d3[2], 0.f), 0u, 0u);
       *reinterpret_cast<uint4*>(sm.g3 + 1 * kAChunk + roff) = make_uint4(0u, 0u, 0u, 0u);
@@ -315,8 +299,6 @@ __global__ void __launch_bounds__(kTile, 2) field_backward_kernel(const __grid_c
       issue_dgrad(tm + kColWork, a_g3, wbase + kWCol3, 64, 16);              // dH2 = dO3 W3c
     });
     tmem_ld64(trow + kColWork, v);
-    if (args.dbg != nullptr && valid)
-      for (int c = 0; c < 8; ++c) args.dbg[i * 64 + 24 + c] = v[c];
     relu_backward_inplace64(sm.h2, roff, v);
     mma_round(sm, phase, [&] {
       issue_wgrad(tm + kColW2c, a_h2, a_h1, 64, have_acc);                   // dW2c += dH2^T H1
@@ -335,11 +317,6 @@ __global__ void __launch_bounds__(kTile, 2) field_backward_kernel(const __grid_c
       float dh0 = 0.f;
       if (valid && args.d_sigma != nullptr)
         dh0 = args.d_sigma[i] * f.density_scale * __expf(fminf(fmaxf(h0, -15.f), 15.f));
-      if (args.dbg != nullptr && valid) {
-        args.dbg[i * 64 + 0] = h0;
-        args.dbg[i * 64 + 1] = dh0;
-        for (int c = 0; c < 16; ++c) args.dbg[i * 64 + 2 + c] = dc[16 + c];
-      }
       *reinterpret_cast<uint4*>(sm.gs + 0 * kAChunk + roff) = make_uint4(
           pack_bf16x2(dh0, dc[16]), pack_bf16x2(dc[17], dc[18]), pack_bf16x2(dc[19], dc[20]), pack_bf16x2(dc[21], dc[22]));
       *reinterpret_cast<uint4*>(sm.gs + 1 * kAChunk + roff) = make_uint4(
@@ -401,13 +378,6 @@ __global__ void __launch_bounds__(kTile, 2) field_backward_kernel(const __grid_c
 
 using namespace hrf;
 
-static float* g_debug_buffer = nullptr;
-// test hook (not part of the reference-facing ABI): per-sample intermediates of the next backward calls
-extern "C" int hrf_debug_set_buffer(void* p) {
-  g_debug_buffer = reinterpret_cast<float*>(p);
-  return 0;
-}
-
 extern "C" int hrf_field_backward(const hrf_field* f, const hrf_samples* s, const hrf_segment_grads* seg_grads,
                                   const float* d_sigma, const float* d_rgb, const void* feat_bf16, float* d_mlp,
                                   void* stream) {
@@ -427,7 +397,6 @@ extern "C" int hrf_field_backward(const hrf_field* f, const hrf_samples* s, cons
   a.d_rgb = d_rgb;
   a.feat_in = reinterpret_cast<const uint4*>(feat_bf16);
   a.d_mlp = d_mlp;
-  a.dbg = g_debug_buffer;
   const int64_t tiles = (s->num_samples + kTile - 1) / kTile;
   const int smem = (int)sizeof(BwdSmem) + 1024;
   const int64_t max_ctas = (int64_t)sm_count() * 2;

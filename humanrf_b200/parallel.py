@@ -1,0 +1,100 @@
+"""Multi-GPU plumbing for the hot path (new work: the reference is single-process, single-GPU).
+
+Training shards ray batches data-parallel, one process per GPU (torch.distributed / NCCL over NVLink):
+every rank holds a full replica, samples its own rays, and the only exchange step is ONE all-reduce (sum) of
+the flat gradient bucket the fused backward kernel wrote (humanrf_b200.training.FusedTrainer).  Ranks may
+keep different numbers of rays after masking, so each rank weights its loss by
+``world * R_local / R_total`` -- the sum over ranks then equals the gradient of the mean loss over the UNION
+batch (HuberLoss(reduction="mean"), trainer.py:89).
+
+Inference shards image tiles (contiguous pixel ranges, exactly the ranges DataLoader.__next__ walks,
+data_loader.py:578-580) or whole (camera, frame) pairs round-robin; no collective on the data path.
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous [start, end) share of n items; shares differ by at most one item."""
+    base, rem = divmod(n, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def deal_round_robin(items: Sequence, rank: int, world: int) -> List:
+    """(camera, frame) pairs of a render sequence dealt round-robin to ranks."""
+    return [x for i, x in enumerate(items) if i % world == rank]
+
+
+def union_batch_loss_scale(num_rays_local: int, device, group=None) -> float:
+    """world * R_local / R_total, so that summing rank gradients and dividing by world gives the gradient of the
+    mean loss over the union of all ranks' rays.  One 8-byte all-reduce."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return 1.0
+    t = torch.tensor([float(num_rays_local)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    total = float(t.item())
+    return dist.get_world_size(group) * num_rays_local / total if total > 0 else 0.0
+
+
+def allreduce_bucket_(flat: torch.Tensor, group=None) -> torch.Tensor:
+    """In-place sum of the flat gradient bucket over the ranks (mean is folded into Adam's grad_scale)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    return flat
+
+
+def broadcast_parameters_(params, src: int = 0, group=None) -> None:
+    """Make every replica start from rank `src`'s parameters."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        for p in params:
+            dist.broadcast(p.data, src=src, group=group)
+
+
+class TileShardedRenderer:
+    """Full-image rendering with the image's pixels split into contiguous ranges over the ranks
+    (Trainer.test / validate, trainer.py:258-526, without the per-batch D2H and the CPU scatter: the image is
+    assembled on the device)."""
+
+    def __init__(self, model, occupancy_grid, rays_per_batch: int = 16384, step: float = 4e-4):
+        self.model, self.og, self.rays_per_batch, self.step = model, occupancy_grid, rays_per_batch, step
+
+    @torch.no_grad()
+    def render_range(self, cam: dict, start: int, end: int, background: float = 0.0) -> torch.Tensor:
+        """cam: dict of the per-image sampler tables for ONE image (frame_numbers, camera_numbers, grid handle,
+        landscape, inverse_krs, camera_origins, aabb, G, width, height).  Returns float32 [end-start, 3]."""
+        from .dataset import ray_sampler_native as rs
+        from .dataset.input_batch import InputBatch
+        from .volume_rendering import prune_samples, render
+
+        dev = cam["aabb"].device
+        out = torch.full((end - start, 3), float(background), dtype=torch.float32, device=dev)
+        empty_rgba = torch.zeros((0, 4), dtype=torch.uint8, device=dev)
+        empty_mask = torch.zeros(0, dtype=torch.bool, device=dev)
+        for s in range(start, end, self.rays_per_batch):
+            e = min(s + self.rays_per_batch, end)
+            idx = torch.arange(s, e, dtype=torch.int64, device=dev)
+            (o, d, _, fn, cn, mm, mask, dist_, rel) = rs.get_samples_occupancy_minmax(
+                empty_rgba, empty_mask, cam["frame_numbers"], cam["camera_numbers"], cam["grid_handles"],
+                cam["landscape"], idx, cam["inverse_krs"], cam["camera_origins"], cam["aabb"], cam["G"], cam["width"],
+                cam["height"], self.step, False)
+            if o.shape[0] == 0:
+                continue
+            ib = InputBatch(ray_origins=o, ray_directions=d, minmaxes=mm, ray_masks=mask.view(-1, 1),
+                            frame_numbers=fn.view(-1, 1), camera_numbers=cn.view(-1, 1),
+                            sample_distances=dist_.view(-1, 1), ray_indices=rel.long(), width=cam["width"],
+                            height=cam["height"])
+            prune_samples(ib, self.model, is_training=False, render_step_size=self.step)
+            bg = torch.full((o.shape[0], 3), float(background), dtype=torch.float32, device=dev)
+            ro = render(ib, self.model, bg, is_training=False, render_step_size=self.step)
+            out[(s - start) + torch.nonzero(mask).view(-1)] = ro.color        # combine_rays_to_image, on device
+        return out
+
+    def render_image_sharded(self, cam: dict, rank: int, world: int, background: float = 0.0):
+        """This rank's tile of the image: returns (start, end, colours)."""
+        start, end = shard_range(cam["width"] * cam["height"], rank, world)
+        return start, end, self.render_range(cam, start, end, background)

@@ -21,6 +21,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
+from .parallel import allreduce_bucket_, union_batch_loss_scale
 from .scene_representation.humanrf import HumanRF
 from .volume_rendering import ray_offsets
 
@@ -64,7 +65,8 @@ class FusedTrainer:
     def current_lr(self) -> float:
         return self.lr * self.lr_decay ** min(self.t / self.max_steps, 1.0)  # run.py:102-104
 
-    def step(self, o, d, frames, t, ri, rgba, num_rays: int, kernel_event=None, return_loss: bool = False):
+    def step(self, o, d, frames, t, ri, rgba, num_rays: int, kernel_event=None, return_loss: bool = False,
+             background: Optional[torch.Tensor] = None):
         """One optimisation step on a ray batch given in InputBatch layout (device tensors).
         Returns the number of kernels launched, or the loss value when return_loss."""
         lib, nat, dev = L.lib(), self.model.native(), t.device
@@ -95,7 +97,7 @@ class FusedTrainer:
         if kernel_event is not None:
             kernel_event.record()
         off = ray_offsets(ri, num_rays)
-        bg = torch.rand((num_rays, 3), device=dev, generator=self.gen)           # trainer.py:237
+        bg = background if background is not None else torch.rand((num_rays, 3), device=dev, generator=self.gen)  # trainer.py:237
         color = torch.empty((num_rays, 3), dtype=torch.float32, device=dev)
         wsum = torch.empty((num_rays, 1), dtype=torch.float32, device=dev)
         L.check(lib.hrf_composite_forward(sigma.data_ptr(), rgb.data_ptr(), t.data_ptr(), off.data_ptr(), num_rays, step,
@@ -109,7 +111,8 @@ class FusedTrainer:
         pc = torch.clamp(wsum, min=0, max=1)
         bce = -(mask * torch.log(pc + 1e-10) + (1 - mask) * torch.log(1 - pc + 1e-10))
         loss = photo + bce.mean() * self.bce_w
-        loss.backward()
+        # data parallel: weight by this rank's share of the union batch (humanrf_b200/parallel.py)
+        (loss * union_batch_loss_scale(num_rays, dev, self.pg) if self.world > 1 else loss).backward()
         # ---- backward: compositing, then the fused field backward into the flat bucket
         d_sigma = torch.empty(n, dtype=torch.float32, device=dev)
         d_rgb = torch.empty((n, 3), dtype=torch.float32, device=dev)
@@ -122,9 +125,7 @@ class FusedTrainer:
         launches += 8 + 12
         # ---- data parallel: one all-reduce of the flat bucket (sum), mean over ranks folded into Adam's grad_scale
         if self.world > 1:
-            import torch.distributed as dist
-
-            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.pg)
+            allreduce_bucket_(self.grad, self.pg)
             launches += 1
         self.apply_adam(1.0 / self.world)
         launches += len(self.params) + 3

@@ -217,9 +217,6 @@ int hrf_selftest_umma(const void* a_bf16 /* [M,K] row-major */, const void* b_bf
                       uint32_t a_lbo, uint32_t a_sbo, uint32_t b_lbo, uint32_t b_sbo,
                       int mn_major /* bit 0: A is MN-major, bit 1: B is MN-major */, void* stream);
 
-/* test hook: float [N,64] device buffer receiving per-sample intermediates of hrf_field_backward (NULL disables) */
-int hrf_debug_set_buffer(void* buffer);
-
 #ifdef __cplusplus
 }
 #endif

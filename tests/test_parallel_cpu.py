@@ -1,0 +1,63 @@
+"""World-size-2 gloo tests (CPU) of the data-parallel host logic: union-batch loss weighting + bucket all-reduce
+reproduce the single-process gradient; tile / sequence sharding covers every item exactly once."""
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from humanrf_b200.parallel import (allreduce_bucket_, broadcast_parameters_, deal_round_robin, shard_range,
+                                   union_batch_loss_scale)
+
+
+def test_shard_range_and_round_robin_cover_everything():
+    for n in (0, 1, 7, 773056):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans[:-1], spans[1:]))
+            assert max(e - s for s, e in spans) - min(e - s for s, e in spans) <= 1
+    seq = [(c, f) for c in range(5) for f in range(7)]
+    dealt = [deal_round_robin(seq, r, 4) for r in range(4)]
+    assert sorted(sum(dealt, [])) == sorted(seq)
+
+
+def _worker(rank, world, port, ray_counts, out):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    w = torch.randn(16, requires_grad=True)                     # replicated "parameters"
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(sum(ray_counts), 16, generator=g)            # the union batch, identical on every rank
+    y = torch.randn(sum(ray_counts), generator=g)
+    lo = sum(ray_counts[:rank])
+    xs, ys = x[lo:lo + ray_counts[rank]], y[lo:lo + ray_counts[rank]]
+    loss = torch.nn.functional.huber_loss(xs @ w, ys, delta=0.01, reduction="mean")   # per-rank mean, as FusedTrainer
+    (loss * union_batch_loss_scale(ray_counts[rank], "cpu")).backward()
+    bucket = w.grad.clone()
+    allreduce_bucket_(bucket)
+    bucket /= world                                              # Adam's grad_scale = 1/world
+    p = torch.full((4,), float(rank))
+    broadcast_parameters_([p], src=0)
+    if rank == 0:
+        w2 = w.detach().clone().requires_grad_(True)
+        torch.nn.functional.huber_loss(x @ w2, y, delta=0.01, reduction="mean").backward()
+        out.put((bucket.numpy(), w2.grad.numpy()))
+    assert float(p.sum()) == 0.0
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_union_batch_weighting_matches_single_process_gloo():
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, (37, 91), out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got, ref = out.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    np.testing.assert_allclose(got, ref, rtol=1e-5, atol=1e-7)
