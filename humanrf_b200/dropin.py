@@ -1,0 +1,27 @@
+"""Makes the reference's own import paths resolve to the B200 implementation, so `humanrf/run.py` and
+`humanrf/trainer.py` run unchanged:
+
+    import humanrf_b200.dropin; humanrf_b200.dropin.install()      # before importing humanrf.run / humanrf.trainer
+
+Only the hot-path modules are replaced; everything else (args, configs, Trainer, DataLoader, dataset IO,
+evaluation) keeps coming from the reference checkout on PYTHONPATH."""
+from __future__ import annotations
+
+import importlib
+import sys
+
+_MAP = {
+    "humanrf.scene_representation.humanrf": "humanrf_b200.scene_representation.humanrf",
+    "humanrf.scene_representation.query_io": "humanrf_b200.scene_representation.query_io",
+    "humanrf.scene_representation.tensor_composition_native": "humanrf_b200.scene_representation.tensor_composition_native",
+    "humanrf.volume_rendering": "humanrf_b200.volume_rendering",
+    "humanrf.input": "humanrf_b200.input",
+    "actorshq.dataset.input_batch": "humanrf_b200.dataset.input_batch",
+    "actorshq.dataset.ray_sampler_native": "humanrf_b200.dataset.ray_sampler_native",
+    "actorshq.dataset.occupancy_grid_native": "humanrf_b200.dataset.occupancy_grid_native",
+}
+
+
+def install() -> None:
+    for ref_name, our_name in _MAP.items():
+        sys.modules[ref_name] = importlib.import_module(our_name)

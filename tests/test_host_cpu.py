@@ -109,3 +109,27 @@ def test_product_does_not_import_oracle():
     for p in (ROOT / "humanrf_b200").rglob("*.py"):
         src = p.read_text()
         assert "import oracle" not in src and "from oracle" not in src, p
+
+
+def test_dropin_maps_reference_import_paths():
+    import sys
+
+    ref = "/root/reference"
+    if not Path(ref).exists():
+        pytest.skip("reference checkout not present (GPU box)")
+    import humanrf_b200.dropin as dropin
+
+    sys.path.insert(0, ref)
+    try:
+        dropin.install()
+        from humanrf.scene_representation.humanrf import HumanRF as A
+        from humanrf_b200.scene_representation.humanrf import HumanRF as B
+        import humanrf.volume_rendering as vr
+        import actorshq.dataset.ray_sampler_native as rs
+
+        assert A is B and hasattr(vr, "prune_samples") and hasattr(rs, "get_samples_occupancy_minmax")
+    finally:
+        sys.path.remove(ref)
+        for k in list(sys.modules):
+            if k.startswith(("humanrf.", "actorshq.")) or k in ("humanrf", "actorshq"):
+                del sys.modules[k]
