@@ -24,4 +24,10 @@ _MAP = {
 
 def install() -> None:
     for ref_name, our_name in _MAP.items():
-        sys.modules[ref_name] = importlib.import_module(our_name)
+        mod = importlib.import_module(our_name)
+        sys.modules[ref_name] = mod
+        parent_name, leaf = ref_name.rsplit(".", 1)
+        try:  # bind the attribute on the (reference's) parent package so `import a.b.c as x` resolves too
+            setattr(importlib.import_module(parent_name), leaf, mod)
+        except ImportError:
+            pass  # reference checkout not on sys.path yet; the sys.modules entry still serves `from a.b.c import x`
