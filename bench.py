@@ -175,8 +175,11 @@ def main():
                                           bg.data_ptr(), color.data_ptr(), wsum.data_ptr(), None, L.stream()))
         launches["n"] += 3
 
+    kept = []
+
     def step_train(ev=None):
         launches["n"] += trainer.step(g["o"], g["d"], g["frames"], g["t"], g["ri"], g["rgba"], RAYS, kernel_event=ev)
+        kept.append(trainer.last["samples"])
 
     step = step_render if args.mode == "render" else step_train
 
@@ -259,7 +262,11 @@ def main():
             "config": {"workload": f"{RAYS} rays x {SPR} samples/ray = {n} samples per GPU, segment_sizes={SEGMENTS} (log2T=18), "
                                    f"8 frames of 15..64, {'forward render' if args.mode == 'render' else 'fwd+bwd+Adam'}",
                        "mode": args.mode, "l2": "flushed between timed steps (256 MiB memset)", "parallelism": f"dp{world}",
-                       "samples_per_s": value * SPR},
+                       "samples_per_s": value * SPR,
+                       **({"samples_after_prune_mean": sum(kept[-args.steps:]) / args.steps,
+                           "note": "prune pass over all 2,097,152 candidates, fwd+bwd over the survivors; the survivor "
+                                   "count drifts because the model really trains (lr=1e-2) on random targets"}
+                          if args.mode == "train" else {})},
             "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "humanrf_b200.volume_rendering.render" if args.mode == "render" else "humanrf_b200.training.FusedTrainer.step"},
             "gpu_launches": gpu_launches,

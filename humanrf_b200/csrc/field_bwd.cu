@@ -8,8 +8,10 @@
 //      packed forward weight blob is re-used as the MN-major B operand of the dgrad GEMMs.
 //      Weight-gradient accumulators live in TMEM for the whole persistent CTA (M=64 tiles)
 //      and are flushed once with fp32 atomics;
-//   3. scatter: per level re-gather the 4x8 corners (needed for the vector gradients),
-//      red.global.add.v2.f32 into the fp32 table gradients, warp-combined adds for the time axis.
+//   3. d(composed features) goes to a level-major [16][N] workspace; a second, high-occupancy kernel
+//      (grid_scatter_kernel: thread = (sample, level)) re-gathers the 4x8 corners (needed for the vector
+//      gradients) and issues red.global.add.v2.f32 into the fp32 table gradients, with warp-combined adds
+//      for the time axis.  (One fused kernel was latency-bound at 12.5 % occupancy: profiles/r1_ncu_full_bwd.)
 #include "field_common.cuh"
 
 namespace hrf {
@@ -44,6 +46,7 @@ struct BwdArgs {
   const float* d_rgb;
   const uint4* feat_in;  // bf16 [N,32] saved by the forward, or NULL (re-encode)
   float* d_mlp;
+  float2* dfeat;  // [16][N] float2 workspace: d(composed features)
 };
 
 // D[128,Nin] = G[128,Kout] * W[Kout,Nin]  : A = gradient tile (K-major), B = forward blob read MN-major
@@ -117,87 +120,122 @@ __device__ __forceinline__ float warp_sum_f(float v) {
   return v;
 }
 __device__ __forceinline__ void red_add2(float* addr, float a, float b) {
-  atomicAdd(reinterpret_cast<float2*>(addr), make_float2(a, b));  // red.global.add.v2.f32
+  // no return value wanted: the vector RED, not the ATOM the float2 atomicAdd intrinsic compiles to
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
 }
 
-// Scatter d(features) of one sample into the table / vector gradients of its segment.
-__device__ __forceinline__ void scatter_sample(const hrf_field& f, const Sample& s, const hrf_segment_grads* sgs,
-                                               const float2* dfeat /* smem, [level][row] */, int row) {
-  const bool valid = s.seg != nullptr;
-  const hrf_segment* sg = valid ? s.seg : f.segments;
-  const hrf_segment_grads gr = sgs[valid ? (int)(s.seg - f.segments) : 0];
-  const uint32_t hmask = sg->hashed_mask;
-  const float* vec = sg->vectors;
-  const VecTap tx = make_tap(s.x, f.vec_res, 0), ty = make_tap(s.y, f.vec_res, 1), tz = make_tap(s.z, f.vec_res, 2),
-               tt = make_tap(s.t, f.vec_res, 3);
-  // time-axis taps are usually identical across the warp (one ray = one frame): combine first
-  const uint32_t full = 0xffffffffu;
-  // (shuffles are executed unconditionally by all 32 lanes; only the comparison is predicated)
-  const uint32_t o0_first = __shfl_sync(full, tt.o0, 0), o1_first = __shfl_sync(full, tt.o1, 0);
-  const unsigned long long vec_first = __shfl_sync(full, (unsigned long long)gr.vectors, 0);
-  const bool same = valid && tt.o0 == o0_first && tt.o1 == o1_first && (unsigned long long)gr.vectors == vec_first;
-  const bool t_uniform = __all_sync(full, same);
-  const int lane = threadIdx.x & 31;
-#pragma unroll 1
-  for (int l = 0; l < HRF_N_LEVELS; ++l) {
-    const float2 dO = valid ? dfeat[l * kTile + row] : make_float2(0.f, 0.f);
-    const float scale = f.level_scale[l];
-    const uint32_t res = f.level_res[l];
-    const uint32_t off = sg->level_offset[l];
-    const uint32_t size = sg->level_size[l];
-    const bool hashed = (hmask >> l) & 1u;
-    const Cell cx = to_cell(scale, s.x), cy = to_cell(scale, s.y), cz = to_cell(scale, s.z), ct = to_cell(scale, s.t);
-    const float2 vx = lerp_tap(vec, tx, 2 * l), vy = lerp_tap(vec, ty, 2 * l), vz = lerp_tap(vec, tz, 2 * l),
-                 vt = lerp_tap(vec, tt, 2 * l);
-    float2 e[4];
-    // grid k pairs with vector: xyz<->t, xyt<->z, yzt<->x, xzt<->y (tensor_composition.cu:49-52)
+// Table / vector gradient scatter (tcnn kernel_grid_backward + compose_tensors_backward,
+// tensor_composition.cu:57-118) as a separate high-occupancy kernel.
+//   thread = (chunk of kChunk consecutive samples, level, grid): blockIdx.y = level*4 + grid.
+// Consecutive samples of a ray are 4e-4 apart, so at most levels they stay in the same grid cell for several
+// samples: the thread keeps the cell's 8 corner indices / values in registers, accumulates w*g per corner while
+// the cell does not change and issues the 8 vector REDs once per RUN of samples (not once per sample).  The
+// same run-length trick applies to the vector taps (the time tap never changes along a ray).  This cuts both
+// the L2 atomics and the gathers by the run length (about 80 samples at level 0, 1.2 at level 15) with no
+// shuffles.  Each grid pairs with exactly one vector axis (xyz<->t, xyt<->z, yzt<->x, xzt<->y), so the
+// (level, grid) threads are independent.
+constexpr int kChunk = 8;
+
+struct ScatterArgs {
+  hrf_field f;
+  hrf_samples s;
+  const hrf_segment_grads* seg_grads;
+  const float2* dfeat;  // [16 levels][N] float2, written by field_backward_kernel
+};
+
+__global__ void __launch_bounds__(256, 3) grid_scatter_kernel(const __grid_constant__ ScatterArgs a) {
+  const hrf_field& f = a.f;
+  const int64_t n = a.s.num_samples;
+  const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * kChunk;
+  if (i0 >= n) return;
+  const int l = blockIdx.y >> 2, k = blockIdx.y & 3;
+  const int axis = (k == 0) ? 3 : (k == 1) ? 2 : (k == 2) ? 0 : 1;  // vector axis paired with grid k
+  const float scale = f.level_scale[l];
+  const uint32_t res = f.level_res[l];
+  const float2* __restrict__ dfl = a.dfeat + (size_t)l * n;
+
+  // state of the current run
+  const hrf_segment* cur_seg = nullptr;
+  uint32_t ca = 0xffffffffu, cb = 0, cc = 0;  // current cell
+  uint32_t idx[8], raw[8];
+  float accx[8], accy[8];
+  float* gtab = nullptr;
+  // vector-tap run
+  uint32_t to0 = 0xffffffffu, to1 = 0;
+  float* gvec = nullptr;
+  float va0 = 0.f, va1 = 0.f, vb0 = 0.f, vb1 = 0.f;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const Cell a = (k == 2) ? cy : cx;
-      const Cell b = (k == 0 || k == 1) ? cy : cz;
-      const Cell c = (k == 0) ? cz : ct;
-      const float2 v = (k == 0) ? vt : (k == 1) ? vz : (k == 2) ? vx : vy;
-      uint32_t idx[8];
-      float w[8];
-      corner_indices(hashed, res, size, a, b, c, idx);
-      corner_weights(a, b, c, w);
-      const uint32_t* tab = sg->grid[k] + off;
-      float* gtab = gr.grid[k] + 2 * (size_t)off;
-      float2 acc = make_float2(0.f, 0.f);
-      const float gx = v.x * dO.x, gy = v.y * dO.y;
+  for (int q = 0; q < 8; ++q) accx[q] = accy[q] = 0.f, idx[q] = raw[q] = 0u;
+
+  auto flush_cell = [&]() {
+    if (gtab != nullptr) {
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
-        const uint32_t raw = __ldg(tab + idx[q]);
-        acc.x = __fmaf_rn(w[q], bf16_lo(raw), acc.x);
-        acc.y = __fmaf_rn(w[q], bf16_hi(raw), acc.y);
-        if (valid && (gx != 0.f || gy != 0.f)) red_add2(gtab + 2 * (size_t)idx[q], w[q] * gx, w[q] * gy);
+        if (accx[q] != 0.f || accy[q] != 0.f) red_add2(gtab + 2 * (size_t)idx[q], accx[q], accy[q]);
+        accx[q] = accy[q] = 0.f;
       }
-      e[k] = acc;
     }
-    if (valid) {
-      // d vectors[axis][i0/i1][2l..2l+1] (tensor_composition.cu:109-111)
-      const float2 dvx = make_float2(e[2].x * dO.x, e[2].y * dO.y), dvy = make_float2(e[3].x * dO.x, e[3].y * dO.y),
-                   dvz = make_float2(e[1].x * dO.x, e[1].y * dO.y);
-      red_add2(gr.vectors + tx.o0 + 2 * l, dvx.x * (1.f - tx.frac), dvx.y * (1.f - tx.frac));
-      red_add2(gr.vectors + tx.o1 + 2 * l, dvx.x * tx.frac, dvx.y * tx.frac);
-      red_add2(gr.vectors + ty.o0 + 2 * l, dvy.x * (1.f - ty.frac), dvy.y * (1.f - ty.frac));
-      red_add2(gr.vectors + ty.o1 + 2 * l, dvy.x * ty.frac, dvy.y * ty.frac);
-      red_add2(gr.vectors + tz.o0 + 2 * l, dvz.x * (1.f - tz.frac), dvz.y * (1.f - tz.frac));
-      red_add2(gr.vectors + tz.o1 + 2 * l, dvz.x * tz.frac, dvz.y * tz.frac);
+  };
+  auto flush_tap = [&]() {
+    if (gvec != nullptr && to0 != 0xffffffffu) {
+      if (va0 != 0.f || va1 != 0.f) red_add2(gvec + to0 + 2 * l, va0, va1);
+      if (vb0 != 0.f || vb1 != 0.f) red_add2(gvec + to1 + 2 * l, vb0, vb1);
     }
-    float2 dvt = make_float2(e[0].x * dO.x, e[0].y * dO.y);
-    if (t_uniform) {
-      const float a0 = warp_sum_f(dvt.x * (1.f - tt.frac)), a1 = warp_sum_f(dvt.y * (1.f - tt.frac));
-      const float b0 = warp_sum_f(dvt.x * tt.frac), b1 = warp_sum_f(dvt.y * tt.frac);
-      if (lane == 0) {
-        red_add2(gr.vectors + tt.o0 + 2 * l, a0, a1);
-        red_add2(gr.vectors + tt.o1 + 2 * l, b0, b1);
+    va0 = va1 = vb0 = vb1 = 0.f;
+  };
+
+  const int cnt = (int)((n - i0) < kChunk ? (n - i0) : kChunk);
+#pragma unroll 1
+  for (int j = 0; j < cnt; ++j) {
+    const int64_t i = i0 + j;
+    const Sample s = load_sample(f, a.s, i, false);
+    if (s.seg == nullptr) continue;
+    const float2 dO = __ldg(dfl + i);
+    const float c0 = (k == 2) ? s.y : s.x;                       // grid coordinates (decomposition4d.py:126-129)
+    const float c1 = (k == 0 || k == 1) ? s.y : s.z;
+    const float c2 = (k == 0) ? s.z : s.t;
+    const float cv = (axis == 0) ? s.x : (axis == 1) ? s.y : (axis == 2) ? s.z : s.t;
+    const Cell A = to_cell(scale, c0), B = to_cell(scale, c1), C = to_cell(scale, c2);
+    if (s.seg != cur_seg || A.g != ca || B.g != cb || C.g != cc) {  // new cell: flush the run, fetch the corners
+      flush_cell();
+      const hrf_segment* sg = s.seg;
+      const uint32_t off = sg->level_offset[l];
+      corner_indices((sg->hashed_mask >> l) & 1u, res, sg->level_size[l], A, B, C, idx);
+      const uint32_t* tab = sg->grid[k] + off;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) raw[q] = __ldg(tab + idx[q]);
+      if (sg != cur_seg) {
+        flush_tap();
+        to0 = 0xffffffffu;
+        gvec = a.seg_grads[(int)(sg - f.segments)].vectors;
       }
-    } else if (valid) {
-      red_add2(gr.vectors + tt.o0 + 2 * l, dvt.x * (1.f - tt.frac), dvt.y * (1.f - tt.frac));
-      red_add2(gr.vectors + tt.o1 + 2 * l, dvt.x * tt.frac, dvt.y * tt.frac);
+      gtab = a.seg_grads[(int)(sg - f.segments)].grid[k] + 2 * (size_t)off;
+      cur_seg = sg, ca = A.g, cb = B.g, cc = C.g;
     }
+    const VecTap tp = make_tap(cv, f.vec_res, axis);
+    const float2 v = lerp_tap(s.seg->vectors, tp, 2 * l);
+    float w[8];
+    corner_weights(A, B, C, w);
+    const float gx = v.x * dO.x, gy = v.y * dO.y;
+    float ex = 0.f, ey = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      accx[q] = __fmaf_rn(w[q], gx, accx[q]);
+      accy[q] = __fmaf_rn(w[q], gy, accy[q]);
+      ex = __fmaf_rn(w[q], bf16_lo(raw[q]), ex);
+      ey = __fmaf_rn(w[q], bf16_hi(raw[q]), ey);
+    }
+    // d vectors[axis][i0/i1][2l..2l+1] = e_k * dOut * (1-frac | frac)   (tensor_composition.cu:109-111)
+    if (tp.o0 != to0 || tp.o1 != to1) {
+      flush_tap();
+      to0 = tp.o0, to1 = tp.o1;
+    }
+    const float dx = ex * dO.x, dy = ey * dO.y;
+    va0 = __fmaf_rn(dx, 1.f - tp.frac, va0), va1 = __fmaf_rn(dy, 1.f - tp.frac, va1);
+    vb0 = __fmaf_rn(dx, tp.frac, vb0), vb1 = __fmaf_rn(dy, tp.frac, vb1);
   }
+  flush_cell();
+  flush_tap();
 }
 
 __global__ void __launch_bounds__(kTile, 2) field_backward_kernel(const __grid_constant__ BwdArgs args) {
@@ -334,14 +372,14 @@ __global__ void __launch_bounds__(kTile, 2) field_backward_kernel(const __grid_c
     });
     have_acc = true;
     {
+      // d(composed features) -> global, level-major [16][N] float2 (coalesced here and in grid_scatter_kernel)
       float df[32];
       tmem_ld32(trow + kColWork, df);
-
-      float2* st = reinterpret_cast<float2*>(sm.h1);  // h1 is dead: stage d(features) as [level][row]
+      if (valid) {
 #pragma unroll
-      for (int l = 0; l < 16; ++l) st[l * kTile + tid] = make_float2(df[2 * l], df[2 * l + 1]);
+        for (int l = 0; l < 16; ++l) args.dfeat[(size_t)l * n + i] = make_float2(df[2 * l], df[2 * l + 1]);
+      }
     }
-    scatter_sample(f, s, args.seg_grads, reinterpret_cast<const float2*>(sm.h1), tid);
   }
 
   if (!weights_ready) mbar_wait(&sm.bar_w, 0);
@@ -380,9 +418,10 @@ using namespace hrf;
 
 extern "C" int hrf_field_backward(const hrf_field* f, const hrf_samples* s, const hrf_segment_grads* seg_grads,
                                   const float* d_sigma, const float* d_rgb, const void* feat_bf16, float* d_mlp,
-                                  void* stream) {
+                                  void* workspace, void* stream) {
   HRF_REQUIRE(f != nullptr && s != nullptr && seg_grads != nullptr, "null argument");
   if (s->num_samples == 0) return 0;
+  HRF_REQUIRE(workspace != nullptr, "hrf_field_backward needs a workspace of 128 bytes per sample");
   HRF_REQUIRE(d_sigma != nullptr || d_rgb != nullptr, "no upstream gradient given");
   if (s->ray_origins == nullptr) {
     HRF_REQUIRE(s->positions && s->frame_numbers, "query form needs positions and frame numbers");
@@ -397,12 +436,24 @@ extern "C" int hrf_field_backward(const hrf_field* f, const hrf_samples* s, cons
   a.d_rgb = d_rgb;
   a.feat_in = reinterpret_cast<const uint4*>(feat_bf16);
   a.d_mlp = d_mlp;
+  a.dfeat = reinterpret_cast<float2*>(workspace);
   const int64_t tiles = (s->num_samples + kTile - 1) / kTile;
   const int smem = (int)sizeof(BwdSmem) + 1024;
   const int64_t max_ctas = (int64_t)sm_count() * 2;
   const int grid = (int)(tiles < max_ctas ? tiles : max_ctas);
   HRF_CUDA(cudaFuncSetAttribute(field_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  field_backward_kernel<<<grid, kTile, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  field_backward_kernel<<<grid, kTile, smem, st>>>(a);
+  HRF_CHECK_LAUNCH();
+  ScatterArgs sa;
+  sa.f = *f;
+  sa.s = *s;
+  sa.seg_grads = seg_grads;
+  sa.dfeat = a.dfeat;
+  {
+    const int64_t chunks = (s->num_samples + kChunk - 1) / kChunk;
+    grid_scatter_kernel<<<dim3((unsigned)((chunks + 255) / 256), HRF_N_LEVELS * 4), 256, 0, st>>>(sa);
+  }
   HRF_CHECK_LAUNCH();
   return 0;
 }

@@ -6,14 +6,18 @@
 // encode -> MLP chain stays in registers / shared memory / TMEM.
 // Reference semantics: humanrf/scene_representation/humanrf.py:158-208,
 // decomposition4d.py:124-135, native/tensor_composition.cu:9-55.
+#include <stdlib.h>
+
 #include "field_common.cuh"
 
 namespace hrf {
 
-struct __align__(1024) FwdSmem {
+
+// One activation buffer serves every layer: a layer's output tile is written over its input tile, which is safe
+// because each thread writes only after the tcgen05.commit barrier of the MMA that read the old tile.
+struct __align__(128) FwdSmem {
   unsigned char w[kWBlobBytes];       // packed weights (TMA bulk copy, once per CTA)
-  unsigned char a[kTile * 32 * 2];    // A tile, K = 32
-  unsigned char h[kTile * 64 * 2];    // A tile, K = 64 (hidden activations)
+  unsigned char a[kTile * 64 * 2];    // A tile: K = 32 layout in the first 8 KB, or K = 64 layout (hidden activations)
   uint64_t bar_w;                     // weights landed
   uint64_t bar_mma;                   // tcgen05.commit arrival
   uint32_t tmem_base;
@@ -84,10 +88,10 @@ __device__ __forceinline__ void store_hidden(unsigned char* hbuf, int row, const
   }
 }
 
-template <bool kSimt>
-__global__ void __launch_bounds__(kTile, 4) field_forward_kernel(const __grid_constant__ FieldArgs args) {
+template <bool kSimt, int kCtasPerSm>
+__global__ void __launch_bounds__(kTile, kCtasPerSm) field_forward_kernel(const __grid_constant__ FieldArgs args) {
   extern __shared__ unsigned char smem_raw[];
-  FwdSmem& sm = *reinterpret_cast<FwdSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  FwdSmem& sm = *reinterpret_cast<FwdSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   const int tid = threadIdx.x;
   const hrf_field& f = args.f;
 
@@ -132,9 +136,9 @@ __global__ void __launch_bounds__(kTile, 4) field_forward_kernel(const __grid_co
     // ---- sigma net: 32 -> 64 (ReLU) -> 16 ------------------------------------------------
     float v[64];
     run_layer<kSimt, 64, 32>(sm, sm.a, kWSig1, phase, v);
-    store_hidden(sm.h, tid, v);
+    store_hidden(sm.a, tid, v);
     float o[16];
-    run_layer<kSimt, 16, 64>(sm, sm.h, kWSig2, phase, o);
+    run_layer<kSimt, 16, 64>(sm, sm.a, kWSig2, phase, o);
     const bool valid = i < n;
     // humanrf.py:184 : density = truncated_exp(h[...,0]) * density_scale  (exp in fp32)
     const float sigma = __expf(o[0]) * f.density_scale;
@@ -167,10 +171,10 @@ __global__ void __launch_bounds__(kTile, 4) field_forward_kernel(const __grid_co
                      pack_bf16x2(o[15], 1.0f));
     }
     run_layer<kSimt, 64, 32>(sm, sm.a, kWCol1, phase, v);
-    store_hidden(sm.h, tid, v);
-    run_layer<kSimt, 64, 64>(sm, sm.h, kWCol2, phase, v);
-    store_hidden(sm.h, tid, v);
-    run_layer<kSimt, 16, 64>(sm, sm.h, kWCol3, phase, o);
+    store_hidden(sm.a, tid, v);
+    run_layer<kSimt, 64, 64>(sm, sm.a, kWCol2, phase, v);
+    store_hidden(sm.a, tid, v);
+    run_layer<kSimt, 16, 64>(sm, sm.a, kWCol3, phase, o);
     if (valid && args.rgb != nullptr) {
       float* rp = args.rgb + 3 * i;
       rp[0] = 1.f / (1.f + __expf(-o[0]));
@@ -216,17 +220,28 @@ extern "C" int hrf_field_forward(const hrf_field* f, const hrf_samples* s, int m
   a.feat = reinterpret_cast<uint4*>(feat_bf16);
   a.mode = mode;
   const int64_t tiles = (s->num_samples + kTile - 1) / kTile;
-  const int smem = (int)sizeof(FwdSmem) + 1024;
+  const int smem = (int)sizeof(FwdSmem) + 128;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int64_t max_ctas = (int64_t)sm_count() * 4;
+  // CTAs per SM, measured on B200 on the bench batch: 4 (118 regs) 1.291 ms, 5 (96 regs) 1.265 ms, 6 (80 regs,
+  // spills, less gather ILP per thread) 1.475 ms.  HRF_FWD_CTAS overrides for experiments.
+  static const int ctas_per_sm = [] {
+    const char* e = getenv("HRF_FWD_CTAS");
+    const int v = e ? atoi(e) : 5;
+    return (v == 4 || v == 6) ? v : 5;
+  }();
+  const int64_t max_ctas = (int64_t)sm_count() * ctas_per_sm;
   const int grid = (int)(tiles < max_ctas ? tiles : max_ctas);
-  if (mlp_impl == 0) {
-    HRF_CUDA(cudaFuncSetAttribute(field_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    field_forward_kernel<false><<<grid, kTile, smem, st>>>(a);
-  } else {
-    HRF_CUDA(cudaFuncSetAttribute(field_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    field_forward_kernel<true><<<grid, kTile, smem, st>>>(a);
-  }
+  auto launch = [&](auto kernel) -> int {
+    HRF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kernel<<<grid, kTile, smem, st>>>(a);
+    return 0;
+  };
+  int rc;
+  if (mlp_impl != 0) rc = launch(field_forward_kernel<true, 4>);
+  else if (ctas_per_sm == 6) rc = launch(field_forward_kernel<false, 6>);
+  else if (ctas_per_sm == 5) rc = launch(field_forward_kernel<false, 5>);
+  else rc = launch(field_forward_kernel<false, 4>);
+  if (rc) return rc;
   HRF_CHECK_LAUNCH();
   return 0;
 }

@@ -273,8 +273,9 @@ class _NativeField:
             i += 1
         sg_dev = torch.from_numpy(np.frombuffer(bytes(sg), dtype=np.uint8).copy()).to(dev)
         d_mlp = torch.zeros(L.MLP_GRAD_ELEMS, dtype=torch.float32, device=dev)
+        ws = torch.empty(int(samples.num_samples) * 32, dtype=torch.float32, device=dev)
         L.check(L.lib().hrf_field_backward(C.byref(self.field), C.byref(samples), sg_dev.data_ptr(), L.ptr(d_sigma),
-                                           L.ptr(d_rgb), L.ptr(feat), d_mlp.data_ptr(), L.stream()))
+                                           L.ptr(d_rgb), L.ptr(feat), d_mlp.data_ptr(), ws.data_ptr(), L.stream()))
         grad_tensors[i].add_(d_mlp[:MLP_SIGMA_PARAMS])
         grad_tensors[i + 1].add_(d_mlp[MLP_SIGMA_PARAMS:])
         return sg_dev  # keep alive until the kernel has run (stream-ordered free is safe, but be explicit)

@@ -60,6 +60,7 @@ class FusedTrainer:
         self.mlp_grad = self.grad[self.offsets[i]:]            # sigma params then colour params: contiguous 10240
         assert self.mlp_grad.numel() == L.MLP_GRAD_ELEMS
         self.last = {}
+        self.profile = False
 
     # ----------------------------------------------------------------------------------------------
     def current_lr(self) -> float:
@@ -71,6 +72,15 @@ class FusedTrainer:
         Returns the number of kernels launched, or the loss value when return_loss."""
         lib, nat, dev = L.lib(), self.model.native(), t.device
         launches = 0
+        marks = [] if self.profile else None
+
+        def mark(name):
+            if marks is not None:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append((name, e))
+
+        mark("start")
         step = self.step_size
         t = t.reshape(-1)
         # ---- prune_samples (volume_rendering.py:42-84): jitter, density-only pass, visibility compaction
@@ -87,15 +97,18 @@ class FusedTrainer:
             L.check(lib.hrf_prune(sigma0.data_ptr(), t.data_ptr(), ri.data_ptr(), off0.data_ptr(), num_rays, step, 1e-4,
                                   1e-4, keep.data_ptr(), kept_off.data_ptr(), t2.data_ptr(), ri2.data_ptr(),
                                   counter.data_ptr(), L.stream()))
+            mark("prune_enqueued")
             kept = int(counter.item())
             t, ri = t2[:kept], ri2[:kept]
             launches += 7
+            mark("prune_synced")
         n = t.shape[0]
         # ---- forward: fused field + compositing
         samples = nat.samples_rays(o, d, frames, t, ri)
         sigma, _, rgb, feat = nat.forward(samples, 1, want_geo=False, want_feat=True)
         if kernel_event is not None:
             kernel_event.record()
+        mark("forward")
         off = ray_offsets(ri, num_rays)
         bg = background if background is not None else torch.rand((num_rays, 3), device=dev, generator=self.gen)  # trainer.py:237
         color = torch.empty((num_rays, 3), dtype=torch.float32, device=dev)
@@ -113,6 +126,7 @@ class FusedTrainer:
         loss = photo + bce.mean() * self.bce_w
         # data parallel: weight by this rank's share of the union batch (humanrf_b200/parallel.py)
         (loss * union_batch_loss_scale(num_rays, dev, self.pg) if self.world > 1 else loss).backward()
+        mark("composite+loss")
         # ---- backward: compositing, then the fused field backward into the flat bucket
         d_sigma = torch.empty(n, dtype=torch.float32, device=dev)
         d_rgb = torch.empty((n, 3), dtype=torch.float32, device=dev)
@@ -120,16 +134,23 @@ class FusedTrainer:
                                            bg.data_ptr(), color.grad.data_ptr(), wsum.grad.reshape(-1).data_ptr(),
                                            d_sigma.data_ptr(), d_rgb.data_ptr(), L.stream()))
         self.grad.zero_()
+        ws = torch.empty(n * 32, dtype=torch.float32, device=dev)
         L.check(lib.hrf_field_backward(C.byref(nat.field), C.byref(samples), self.sg_dev.data_ptr(), d_sigma.data_ptr(),
-                                       d_rgb.data_ptr(), feat.data_ptr(), self.mlp_grad.data_ptr(), L.stream()))
+                                       d_rgb.data_ptr(), feat.data_ptr(), self.mlp_grad.data_ptr(), ws.data_ptr(),
+                                       L.stream()))
         launches += 8 + 12
+        mark("backward")
         # ---- data parallel: one all-reduce of the flat bucket (sum), mean over ranks folded into Adam's grad_scale
         if self.world > 1:
             allreduce_bucket_(self.grad, self.pg)
             launches += 1
         self.apply_adam(1.0 / self.world)
         launches += len(self.params) + 3
+        mark("allreduce+adam")
         self.last = {"samples": n, "loss": loss.detach()}
+        if marks is not None:
+            torch.cuda.synchronize()
+            self.last["phases_ms"] = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(marks[:-1], marks[1:])}
         if return_loss:
             return float(loss.item())
         return launches

@@ -181,7 +181,7 @@ int hrf_field_backward(const hrf_field* f, const hrf_samples* s, const hrf_segme
                        const float* d_sigma /* [N] */, const float* d_rgb /* [N,3] or NULL */,
                        const void* feat_bf16 /* [N,32] from hrf_field_forward, or NULL to re-encode */,
                        float* d_mlp /* fp32 [10240]: sigma W1,W2, colour W1,W2,W3 row-major [out,in] */,
-                       void* stream);
+                       void* workspace /* 128 bytes per sample: d(composed features), level-major */, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * tensor_composition_native parity (tensor_composition.cu:120-219): stand-alone fwd/bwd of
