@@ -100,3 +100,38 @@ def test_oracle_bf16_mode_close_to_fp32_mode():
         s16, _, c16 = om16.forward(pos, dirs, fr)
     assert ((s32 - s16).abs() / s32).max() < 0.1 and (c32 - c16).abs().max() < 2e-2
     assert s32.std() / s32.mean() > 0.2, "synthetic parameters must give non-degenerate densities"
+
+
+def test_config0_cpu_plumbing_sampler_to_input_batch_to_merge():
+    """BASELINE configs[0]: oracle sampler -> InputBatch -> merge_input_batches on the CPU, against frozen golden counts."""
+    from pathlib import Path
+
+    from humanrf_b200.dataset.input_batch import InputBatch
+    from humanrf_b200.input import merge_input_batches
+    from scene import make_scene
+
+    G0 = np.load(Path(__file__).resolve().parent / "golden" / "sampler_config0.npz")
+    sc = make_scene(num_images=1, width=96, height=72, G=64, portrait_every=0, seed=3)
+    batches = []
+    for name, occ, step in (("occ", True, 4e-4), ("aabb", False, 4e-3)):
+        o, d, rgba, fn, cn, mm, mask, t, rel = S.get_data(sc["rgba"], sc["light_mask"], sc["frame_numbers"], sc["camera_numbers"],
+                                                          sc["grids"], sc["landscape"], G0["idx"], sc["inverse_krs"],
+                                                          sc["camera_origins"], sc["aabb"], sc["G"], 96, 72, step, False, occupancy=occ)
+        np.testing.assert_array_equal(mask, G0[f"{name}_mask"])
+        np.testing.assert_array_equal(mm, G0[f"{name}_minmax"])
+        np.testing.assert_array_equal(d, G0[f"{name}_dirs"])
+        np.testing.assert_array_equal(np.bincount(rel, minlength=mm.shape[0]), G0[f"{name}_counts"])
+        np.testing.assert_array_equal(t[:64], G0[f"{name}_t_head"])
+        assert (np.diff(rel) >= 0).all() and (mm[:, 0] < mm[:, 1]).all()
+        tt = torch.from_numpy
+        batches.append(InputBatch(ray_origins=tt(o), ray_directions=tt(d), minmaxes=tt(mm), rgba=tt(rgba),
+                                  ray_masks=tt(mask).view(-1, 1), frame_numbers=tt(fn).view(-1, 1),
+                                  unique_frame_numbers=torch.unique(tt(fn)).view(-1, 1), camera_numbers=tt(cn).view(-1, 1),
+                                  sample_distances=tt(t).view(-1, 1), ray_indices=tt(rel).long(), width=96, height=72))
+    merged = merge_input_batches(batches, max_num_samples=int(0.8 * sum(b.num_samples for b in batches)))
+    assert merged.num_rays <= sum(b.num_rays for b in batches) and merged.num_samples <= 0.8 * sum(b.num_samples for b in batches)
+    assert merged.ray_indices.max() < merged.num_rays and (merged.ray_indices[1:] >= merged.ray_indices[:-1]).all()
+    # input.py:41 keeps `cumsum < cutoff`, i.e. one True fewer than surviving rays (reference quirk, mirrored)
+    assert int(merged.ray_masks.sum()) in (merged.num_rays - 1, merged.num_rays)
+    # AABB rays are a superset of the occupancy rays and their intervals contain the occupancy intervals
+    assert (G0["aabb_mask"] | ~G0["occ_mask"]).all()
