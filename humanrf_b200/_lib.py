@@ -61,6 +61,8 @@ _SIGNATURES = {
     "hrf_sampler_workspace_bytes": (i64, [i64]),
     "hrf_sampler_samples": (C.c_int, [C.POINTER(SamplerParams), i64, vp, vp, vp, vp, vp, vp, vp, vp]),
     "hrf_field_forward": (C.c_int, [C.POINTER(Field), C.POINTER(Samples), C.c_int, C.c_int, vp, vp, vp, vp, vp]),
+    "hrf_density_early_stop_workspace_bytes": (i64, [i64]),
+    "hrf_field_density_early_stop": (C.c_int, [C.POINTER(Field), C.POINTER(Samples), vp, i64, f32, f32, vp, vp, vp]),
     "hrf_ray_offsets": (C.c_int, [vp, i64, i64, vp, vp]),
     "hrf_prune": (C.c_int, [vp, vp, vp, vp, i64, f32, f32, f32, vp, vp, vp, vp, vp, vp]),
     "hrf_composite_forward": (C.c_int, [vp, vp, vp, vp, i64, f32, vp, vp, vp, vp, vp]),

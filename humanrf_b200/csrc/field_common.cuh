@@ -30,9 +30,20 @@ __device__ __forceinline__ uint32_t w_off(int n, int k, int N) {
   return (uint32_t)((k >> 3) * (N >> 3) + (n >> 3)) * 128u + (uint32_t)(n & 7) * 16u + (uint32_t)(k & 7) * 2u;
 }
 
+// Optional early-stop schedule of the density-only pass (see field_fwd.cu).
+struct EarlyStop {
+  const int32_t* ray_offsets;      // [R+1] first sample of each ray; NULL disables the schedule
+  int64_t num_rays;
+  float* ray_depth;                // [R] accumulated optical depth sum(sigma*step) of the finished chunks (zeroed)
+  unsigned long long* counter;     // work-item counter (zeroed)
+  const int32_t* max_chunks;       // device scalar: ceil(max samples per ray / 128)
+  float step, stop_depth;
+};
+
 struct FieldArgs {
   hrf_field f;
   hrf_samples s;
+  EarlyStop es;
   float* sigma;
   uint32_t* geo;   // bf16 [N,16] viewed as u32 pairs
   float* rgb;

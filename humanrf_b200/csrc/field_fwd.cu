@@ -21,7 +21,16 @@ struct __align__(128) FwdSmem {
   uint64_t bar_w;                     // weights landed
   uint64_t bar_mma;                   // tcgen05.commit arrival
   uint32_t tmem_base;
+  // early-stop schedule: the current work item, published by thread 0
+  int64_t item_start, item_end;
+  int32_t item_ray, item_skip;
 };
+
+__device__ __forceinline__ float warp_sum_fwd(float v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
 
 template <int N>
 __device__ __forceinline__ void tmem_load_row(uint32_t taddr, float* v) {
@@ -119,11 +128,58 @@ __global__ void __launch_bounds__(kTile, kCtasPerSm) field_forward_kernel(const 
 
   const int64_t n = args.s.num_samples;
   const int64_t num_tiles = (n + kTile - 1) / kTile;
-  for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-    const int64_t i = tile * kTile + tid;
-    const Sample s = load_sample(f, args.s, i, args.mode != 0);
+  // Early-stop schedule (density-only pass of prune_samples, volume_rendering.py:66-84).  Work items are
+  // (chunk k, ray r) = samples [off[r]+128k, off[r]+128(k+1)) of ray r, pulled from a global counter in the order
+  // c = k*R + r, i.e. all rays' first chunks, then all second chunks, ...  Every finished item adds its optical depth
+  // sum(sigma*step) to ray_depth[r].  render_visibility drops every sample whose transmittance
+  // T = exp(-depth before it) is below 1e-4 whatever its own density, so an item whose ray has already
+  // accumulated depth >= stop_depth (exp(-9.4) = 8.3e-5 < 1e-4, a margin over float rounding) is provably dead:
+  // its densities are never evaluated and are reported as 0.  The depth seen at pull time only contains earlier
+  // chunks of the same ray, so the kept set is exactly the reference's.
+  const bool es = args.es.ray_offsets != nullptr;
+  int64_t tile = blockIdx.x;
+  while (true) {
+    int64_t i;
+    bool valid;
+    int ray = -1;
+    if (!es) {
+      if (tile >= num_tiles) break;
+      i = tile * kTile + tid;
+      valid = i < n;
+      tile += gridDim.x;
+    } else {
+      __syncthreads();  // everybody is done with the previous item's shared fields
+      if (tid == 0) {
+        const unsigned long long R = (unsigned long long)args.es.num_rays;
+        const unsigned long long total = (unsigned long long)__ldg(args.es.max_chunks) * R;
+        sm.item_start = -1;
+        while (true) {
+          const unsigned long long c = atomicAdd(args.es.counter, 1ull);
+          if (c >= total) break;
+          const int r = (int)(c % R);
+          const int64_t k = (int64_t)(c / R);
+          const int64_t b = __ldg(args.es.ray_offsets + r), e = __ldg(args.es.ray_offsets + r + 1);
+          if (b + k * kTile >= e) continue;  // this ray has no chunk k
+          sm.item_start = b + k * kTile;
+          sm.item_end = e;
+          sm.item_ray = r;
+          sm.item_skip = __ldcg(args.es.ray_depth + r) >= args.es.stop_depth;
+          break;
+        }
+      }
+      __syncthreads();
+      if (sm.item_start < 0) break;
+      i = sm.item_start + tid;
+      valid = i < sm.item_end;
+      ray = sm.item_ray;
+      if (sm.item_skip) {
+        if (valid && args.sigma != nullptr) args.sigma[i] = 0.f;
+        continue;
+      }
+    }
+    const Sample s = load_sample(f, args.s, valid ? i : n, args.mode != 0);
     encode_to_smem(f, s, sm.a, tid);
-    if (args.feat != nullptr && i < args.s.num_samples) {
+    if (args.feat != nullptr && valid) {
       const uint32_t ro = a_row_off(tid);
 #pragma unroll
       for (int kg = 0; kg < 4; ++kg) args.feat[i * 4 + kg] = *reinterpret_cast<const uint4*>(sm.a + kg * kAChunk + ro);
@@ -139,9 +195,12 @@ __global__ void __launch_bounds__(kTile, kCtasPerSm) field_forward_kernel(const 
     store_hidden(sm.a, tid, v);
     float o[16];
     run_layer<kSimt, 16, 64>(sm, sm.a, kWSig2, phase, o);
-    const bool valid = i < n;
     // humanrf.py:184 : density = truncated_exp(h[...,0]) * density_scale  (exp in fp32)
     const float sigma = __expf(o[0]) * f.density_scale;
+    if (es) {  // publish this item's optical depth
+      const float part = warp_sum_fwd(valid ? sigma * args.es.step : 0.f);
+      if ((tid & 31) == 0 && part > 0.f) atomicAdd(args.es.ray_depth + ray, part);
+    }
     if (valid) {
       if (args.sigma != nullptr) args.sigma[i] = sigma;
       if (args.geo != nullptr) {
@@ -196,8 +255,34 @@ __global__ void __launch_bounds__(kTile, kCtasPerSm) field_forward_kernel(const 
 
 using namespace hrf;
 
-extern "C" int hrf_field_forward(const hrf_field* f, const hrf_samples* s, int mode, int mlp_impl, float* sigma,
-                                 void* geo_bf16, float* rgb, void* feat_bf16, void* stream) {
+static int launch_field_forward(const FieldArgs& a, int mlp_impl, cudaStream_t st, bool persistent_full) {
+  const int64_t tiles = (a.s.num_samples + kTile - 1) / kTile;
+  const int smem = (int)sizeof(FwdSmem) + 128;
+  // CTAs per SM, measured on B200 on the bench batch: 4 (118 regs) 1.291 ms, 5 (96 regs) 1.265 ms, 6 (80 regs,
+  // spills, less gather ILP per thread) 1.475 ms.  HRF_FWD_CTAS overrides for experiments.
+  static const int ctas_per_sm = [] {
+    const char* e = getenv("HRF_FWD_CTAS");
+    const int v = e ? atoi(e) : 5;
+    return (v == 4 || v == 6) ? v : 5;
+  }();
+  const int64_t max_ctas = (int64_t)sm_count() * ctas_per_sm;
+  const int grid = (int)((tiles < max_ctas && !persistent_full) ? tiles : max_ctas);
+  auto launch = [&](auto kernel) -> int {
+    HRF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    kernel<<<grid, kTile, smem, st>>>(a);
+    return 0;
+  };
+  int rc;
+  if (mlp_impl != 0) rc = launch(field_forward_kernel<true, 4>);
+  else if (ctas_per_sm == 6) rc = launch(field_forward_kernel<false, 6>);
+  else if (ctas_per_sm == 4) rc = launch(field_forward_kernel<false, 4>);
+  else rc = launch(field_forward_kernel<false, 5>);
+  if (rc) return rc;
+  HRF_CHECK_LAUNCH();
+  return 0;
+}
+
+static int check_field_args(const hrf_field* f, const hrf_samples* s, int mode) {
   HRF_REQUIRE(f != nullptr && s != nullptr, "null field/samples");
   HRF_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (density) or 1 (density+radiance)");
   HRF_REQUIRE(s->num_samples >= 0, "negative sample count");
@@ -210,38 +295,66 @@ extern "C" int hrf_field_forward(const hrf_field* f, const hrf_samples* s, int m
     HRF_REQUIRE(s->positions && s->frame_numbers, "query form needs positions and frame numbers");
     HRF_REQUIRE(mode == 0 || s->directions, "radiance queries need directions");
   }
+  return 0;
+}
+
+extern "C" int hrf_field_forward(const hrf_field* f, const hrf_samples* s, int mode, int mlp_impl, float* sigma,
+                                 void* geo_bf16, float* rgb, void* feat_bf16, void* stream) {
+  if (int rc = check_field_args(f, s, mode)) return rc;
   if (s->num_samples == 0) return 0;
   FieldArgs a;
   a.f = *f;
   a.s = *s;
+  a.es = EarlyStop{};
   a.sigma = sigma;
   a.geo = reinterpret_cast<uint32_t*>(geo_bf16);
   a.rgb = rgb;
   a.feat = reinterpret_cast<uint4*>(feat_bf16);
   a.mode = mode;
-  const int64_t tiles = (s->num_samples + kTile - 1) / kTile;
-  const int smem = (int)sizeof(FwdSmem) + 128;
+  return launch_field_forward(a, mlp_impl, reinterpret_cast<cudaStream_t>(stream), false);
+}
+
+namespace hrf {
+__global__ void ray_max_chunks_kernel(const int32_t* __restrict__ off, int64_t num_rays, int32_t* __restrict__ out) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int c = 0;
+  if (r < num_rays) c = (off[r + 1] - off[r] + kTile - 1) / kTile;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) c = max(c, __shfl_xor_sync(0xffffffffu, c, d));
+  if ((threadIdx.x & 31) == 0 && c > 0) atomicMax(out, c);
+}
+}  // namespace hrf
+
+extern "C" int64_t hrf_density_early_stop_workspace_bytes(int64_t num_rays) { return 4 * num_rays + 64; }
+
+extern "C" int hrf_field_density_early_stop(const hrf_field* f, const hrf_samples* s, const int32_t* ray_offsets,
+                                            int64_t num_rays, float step, float stop_depth, float* sigma,
+                                            void* workspace, void* stream) {
+  if (int rc = check_field_args(f, s, 0)) return rc;
+  HRF_REQUIRE(s->ray_origins != nullptr, "the early-stop density pass needs the ray-batch form");
+  HRF_REQUIRE(ray_offsets != nullptr && sigma != nullptr && workspace != nullptr, "null argument");
+  HRF_REQUIRE(step > 0.f && stop_depth > 9.2104f, "stop_depth must stay above -ln(1e-4) so the kept set is exact");
+  if (s->num_samples == 0 || num_rays == 0) return 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  // CTAs per SM, measured on B200 on the bench batch: 4 (118 regs) 1.291 ms, 5 (96 regs) 1.265 ms, 6 (80 regs,
-  // spills, less gather ILP per thread) 1.475 ms.  HRF_FWD_CTAS overrides for experiments.
-  static const int ctas_per_sm = [] {
-    const char* e = getenv("HRF_FWD_CTAS");
-    const int v = e ? atoi(e) : 5;
-    return (v == 4 || v == 6) ? v : 5;
-  }();
-  const int64_t max_ctas = (int64_t)sm_count() * ctas_per_sm;
-  const int grid = (int)(tiles < max_ctas ? tiles : max_ctas);
-  auto launch = [&](auto kernel) -> int {
-    HRF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    kernel<<<grid, kTile, smem, st>>>(a);
-    return 0;
-  };
-  int rc;
-  if (mlp_impl != 0) rc = launch(field_forward_kernel<true, 4>);
-  else if (ctas_per_sm == 6) rc = launch(field_forward_kernel<false, 6>);
-  else if (ctas_per_sm == 5) rc = launch(field_forward_kernel<false, 5>);
-  else rc = launch(field_forward_kernel<false, 4>);
-  if (rc) return rc;
+  char* ws = reinterpret_cast<char*>(workspace);
+  HRF_CUDA(cudaMemsetAsync(ws, 0, (size_t)hrf_density_early_stop_workspace_bytes(num_rays), st));
+  FieldArgs a;
+  a.f = *f;
+  a.s = *s;
+  a.es.ray_offsets = ray_offsets;
+  a.es.num_rays = num_rays;
+  a.es.ray_depth = reinterpret_cast<float*>(ws + 64);
+  a.es.counter = reinterpret_cast<unsigned long long*>(ws);
+  a.es.max_chunks = reinterpret_cast<const int32_t*>(ws + 16);
+  a.es.step = step;
+  a.es.stop_depth = stop_depth;
+  a.sigma = sigma;
+  a.geo = nullptr;
+  a.rgb = nullptr;
+  a.feat = nullptr;
+  a.mode = 0;
+  ray_max_chunks_kernel<<<(unsigned)((num_rays + 255) / 256), 256, 0, st>>>(ray_offsets, num_rays,
+                                                                           reinterpret_cast<int32_t*>(ws + 16));
   HRF_CHECK_LAUNCH();
-  return 0;
+  return launch_field_forward(a, 0, st, true);
 }

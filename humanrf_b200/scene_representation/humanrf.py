@@ -259,6 +259,19 @@ class _NativeField:
                                           L.ptr(geo), L.ptr(rgb), L.ptr(feat), L.stream()))
         return sigma, geo, rgb, feat
 
+    def density_early_stop(self, samples: L.Samples, ray_offsets: torch.Tensor, num_rays: int, step: float,
+                           stop_depth: float = 9.4) -> torch.Tensor:
+        """Density-only pass for prune_samples with the exact early stop (hrf_field_density_early_stop)."""
+        dev = self._device()
+        n = int(samples.num_samples)
+        sigma = torch.empty(n, dtype=torch.float32, device=dev)
+        lib = L.lib()
+        ws = torch.empty(int(lib.hrf_density_early_stop_workspace_bytes(num_rays)), dtype=torch.uint8, device=dev)
+        L.check(lib.hrf_field_density_early_stop(C.byref(self.field), C.byref(samples), ray_offsets.data_ptr(), num_rays,
+                                                 float(step), float(stop_depth), sigma.data_ptr(), ws.data_ptr(),
+                                                 L.stream()))
+        return sigma
+
     def backward(self, samples: L.Samples, d_sigma, d_rgb, feat, grad_tensors: List[torch.Tensor]):
         """grad_tensors: fp32 buffers in hot_parameters() order (accumulated into)."""
         m = self.model

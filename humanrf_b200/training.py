@@ -87,8 +87,8 @@ class FusedTrainer:
         if self.prune:
             t = t + torch.rand(t.shape, device=dev, generator=self.gen) * step
             n0 = t.shape[0]
-            sigma0, _, _, _ = nat.forward(nat.samples_rays(o, d, frames, t, ri), 0, want_geo=False, want_feat=False)
             off0 = ray_offsets(ri, num_rays)
+            sigma0 = nat.density_early_stop(nat.samples_rays(o, d, frames, t, ri), off0, num_rays, step)
             keep = torch.empty(n0, dtype=torch.uint8, device=dev)
             kept_off = torch.empty(num_rays + 1, dtype=torch.int32, device=dev)
             t2 = torch.empty(n0, dtype=torch.float32, device=dev)
@@ -100,8 +100,9 @@ class FusedTrainer:
             mark("prune_enqueued")
             kept = int(counter.item())
             t, ri = t2[:kept], ri2[:kept]
-            launches += 7
+            launches += 9
             mark("prune_synced")
+            off = kept_off                                   # hrf_prune's scan IS the ray-offset table of the survivors
         n = t.shape[0]
         # ---- forward: fused field + compositing
         samples = nat.samples_rays(o, d, frames, t, ri)
@@ -109,7 +110,8 @@ class FusedTrainer:
         if kernel_event is not None:
             kernel_event.record()
         mark("forward")
-        off = ray_offsets(ri, num_rays)
+        if not self.prune:
+            off = ray_offsets(ri, num_rays)
         bg = background if background is not None else torch.rand((num_rays, 3), device=dev, generator=self.gen)  # trainer.py:237
         color = torch.empty((num_rays, 3), dtype=torch.float32, device=dev)
         wsum = torch.empty((num_rays, 1), dtype=torch.float32, device=dev)

@@ -67,8 +67,9 @@ def prune_samples(input_batch: InputBatch, scene_representation: HumanRF, is_tra
     o, d, fr, t, ri = _ray_arrays(ib)
     n, num_rays = t.shape[0], ib.num_rays
     dev = t.device
-    sigma, _, _, _ = nat.forward(nat.samples_rays(o, d, fr, t, ri), 0, want_geo=False, want_feat=False)
     off = ray_offsets(ri, num_rays)
+    # density-only pass; chunks of a ray behind an already opaque prefix are provably pruned and are not evaluated
+    sigma = nat.density_early_stop(nat.samples_rays(o, d, fr, t, ri), off, num_rays, render_step_size)
     keep = torch.empty(n, dtype=torch.uint8, device=dev)
     kept_off = torch.empty(num_rays + 1, dtype=torch.int32, device=dev)
     out_t = torch.empty(n, dtype=torch.float32, device=dev)

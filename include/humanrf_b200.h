@@ -142,6 +142,17 @@ int hrf_field_forward(const hrf_field* f, const hrf_samples* s, int mode, int ml
                       float* rgb /* [N,3] */, void* feat_bf16 /* [N,32] composed features saved for backward, or NULL */,
                       void* stream);
 
+/* Density-only pass of prune_samples (volume_rendering.py:66-84) with an exact early stop: ray chunks are
+ * evaluated front to back; once a ray's accumulated optical depth makes every later sample fail nerfacc's
+ * transmittance test (T < 1e-4) those samples are reported with sigma = 0 without being evaluated.  The kept
+ * set of hrf_prune on this sigma equals the one on the fully evaluated sigma.  workspace: device scratch of
+ * hrf_density_early_stop_workspace_bytes(num_rays) bytes. */
+int64_t hrf_density_early_stop_workspace_bytes(int64_t num_rays);
+int hrf_field_density_early_stop(const hrf_field* f, const hrf_samples* s /* ray-batch form */,
+                                 const int32_t* ray_offsets /* [R+1] */, int64_t num_rays, float step,
+                                 float stop_depth /* > -ln(1e-4); 9.4 recommended */, float* sigma /* [N] */,
+                                 void* workspace, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Compositing.  Replaces nerfacc.render_visibility / render_weight_from_density /
  * accumulate_along_rays as called from humanrf/volume_rendering.py:75-84,123-145.

@@ -101,3 +101,38 @@ def test_composite_forward_backward(cuda, with_bg):
     gs, gc = s64.grad.numpy(), c64.grad.numpy()
     np.testing.assert_allclose(d_rgb.cpu().numpy(), gc, rtol=3e-4, atol=1e-6)
     np.testing.assert_allclose(d_sigma.cpu().numpy(), gs, rtol=2e-3, atol=2e-6 * np.abs(gs).max())
+
+
+def test_early_stop_density_pass_gives_the_same_kept_set(cuda):
+    """hrf_field_density_early_stop skips chunks behind an opaque prefix; hrf_prune on its sigma must keep exactly the
+    samples it keeps on the fully evaluated sigma, and the evaluated densities must be bit-identical."""
+    from helpers import make_pair
+
+    om, m, frames = make_pair((6,), table_std=6.0)
+    m.density_scale = 400.0                      # opaque quickly: T < 1e-4 after ~60 samples
+    m._native = None
+    nat = m.native()
+    for ragged in (False, True):
+        b = synthetic_rays(300, 700, frames, seed=5, ragged=ragged)
+        g = {k: v.to(cuda).contiguous() for k, v in b.items() if k in ("o", "d", "frames", "t", "ri")}
+        s = nat.samples_rays(g["o"], g["d"], g["frames"], g["t"], g["ri"])
+        full, _, _, _ = nat.forward(s, 0, want_geo=False, want_feat=False)
+        off = ray_offsets(g["ri"], 300)
+        es = nat.density_early_stop(s, off, 300, 4e-4)
+        torch.cuda.synchronize()
+        skipped = (es == 0) & (full != 0)
+        assert skipped.any(), "the schedule never skipped anything"
+        torch.testing.assert_close(es[~skipped], full[~skipped], rtol=0, atol=0)
+        masks = []
+        for sig in (full, es):
+            n = sig.shape[0]
+            keep = torch.empty(n, dtype=torch.uint8, device=cuda)
+            kept_off = torch.empty(301, dtype=torch.int32, device=cuda)
+            ot, ori = torch.empty(n, device=cuda), torch.empty(n, dtype=torch.int64, device=cuda)
+            cnt = torch.zeros(1, dtype=torch.int64, device=cuda)
+            L.check(L.lib().hrf_prune(sig.data_ptr(), g["t"].data_ptr(), g["ri"].data_ptr(), off.data_ptr(), 300, 4e-4, 1e-4,
+                                      1e-4, keep.data_ptr(), kept_off.data_ptr(), ot.data_ptr(), ori.data_ptr(),
+                                      cnt.data_ptr(), L.stream()))
+            masks.append(keep.clone())
+        assert torch.equal(masks[0], masks[1])
+        print(f"ragged={ragged}: {int(skipped.sum())} of {full.numel()} densities skipped, kept {int(masks[0].sum())}")
