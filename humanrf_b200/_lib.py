@@ -15,8 +15,7 @@ import torch
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libhumanrf_b200.so"
 N_LEVELS = 16
-MLP_BLOB_BYTES = 20480
-MLP_GRAD_ELEMS = 10240
+MLP_BLOB_BYTES = 22528
 
 vp, i64, i32, u32, u64, f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_uint32, C.c_uint64, C.c_float
 
@@ -36,13 +35,14 @@ class Segment(C.Structure):
 class Field(C.Structure):
     _fields_ = [("segments", vp), ("frame_to_segment", vp), ("frame_to_tlocal", vp), ("mlp_blob", vp),
                 ("level_scale", f32 * N_LEVELS), ("level_res", u32 * N_LEVELS), ("num_segments", i32),
-                ("lut_size", i32), ("vec_res", i32), ("density_scale", f32)]
+                ("lut_size", i32), ("vec_res", i32), ("density_scale", f32), ("camera_embeddings", vp),
+                ("camera_embedding_dim", i32), ("num_cameras", i32), ("color_in_width", i32)]
 
 
 class Samples(C.Structure):
     _fields_ = [("positions", vp), ("directions", vp), ("frame_numbers", vp), ("ray_origins", vp),
                 ("ray_directions", vp), ("ray_frame_numbers", vp), ("sample_distances", vp), ("ray_indices", vp),
-                ("num_samples", i64)]
+                ("num_samples", i64), ("camera_numbers", vp), ("ray_camera_numbers", vp), ("use_camera_embeddings", i32)]
 
 
 class SegmentGrads(C.Structure):
@@ -67,7 +67,7 @@ _SIGNATURES = {
     "hrf_prune": (C.c_int, [vp, vp, vp, vp, i64, f32, f32, f32, vp, vp, vp, vp, vp, vp]),
     "hrf_composite_forward": (C.c_int, [vp, vp, vp, vp, i64, f32, vp, vp, vp, vp, vp]),
     "hrf_composite_backward": (C.c_int, [vp, vp, vp, vp, i64, f32, vp, vp, vp, vp, vp, vp]),
-    "hrf_field_backward": (C.c_int, [C.POINTER(Field), C.POINTER(Samples), vp, vp, vp, vp, vp, vp, vp]),
+    "hrf_field_backward": (C.c_int, [C.POINTER(Field), C.POINTER(Samples), vp, vp, vp, vp, vp, vp, vp, vp]),
     "hrf_compose_tensors_forward": (C.c_int, [vp, vp, vp, vp, vp, vp, i64, C.c_int, C.c_int, vp, vp]),
     "hrf_compose_tensors_backward": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, i64, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),
     "hrf_adam_step": (C.c_int, [vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, C.c_int, f32, vp]),

@@ -19,7 +19,7 @@ namespace hrf {
 struct __align__(1024) BwdSmem {
   unsigned char w[kWBlobBytes];
   unsigned char feat[kTile * 32 * 2];  // composed features            (A32)
-  unsigned char cin[kTile * 32 * 2];   // colour-net input              (A32)
+  unsigned char cin[kTile * 48 * 2];   // colour-net input              (A32 / A48)
   unsigned char hs[kTile * 64 * 2];    // sigma hidden, then d(hidden)  (A64)
   unsigned char h1[kTile * 64 * 2];    // colour hidden 1, then its gradient, then dFeat staging
   unsigned char h2[kTile * 64 * 2];    // colour hidden 2, then its gradient
@@ -33,9 +33,9 @@ struct __align__(1024) BwdSmem {
 constexpr uint32_t kColWork = 0;     // 64 cols: layer outputs / dgrad results
 constexpr uint32_t kColW1s = 64;     // dW1s   [64 out, 32 in]
 constexpr uint32_t kColW2s = 96;     // dW2s^T [64 in, 16 out]
-constexpr uint32_t kColW1c = 112;    // dW1c   [64 out, 32 in]
-constexpr uint32_t kColW2c = 144;    // dW2c   [64 out, 64 in]
-constexpr uint32_t kColW3c = 208;    // dW3c^T [64 in, 16 out]
+constexpr uint32_t kColW1c = 112;    // dW1c   [64 out, 32|48 in]
+constexpr uint32_t kColW2c = 160;    // dW2c   [64 out, 64 in]
+constexpr uint32_t kColW3c = 224;    // dW3c^T [64 in, 16 out]
 constexpr uint32_t kTmemCols = 256;
 
 struct BwdArgs {
@@ -46,7 +46,10 @@ struct BwdArgs {
   const float* d_rgb;
   const uint4* feat_in;  // bf16 [N,32] saved by the forward, or NULL (re-encode)
   float* d_mlp;
+  float* d_emb;   // camera-embedding gradient [num_cameras, E] or NULL
   float2* dfeat;  // [16][N] float2 workspace: d(composed features)
+  float4* pos4;   // [N] normalised (x,y,z,t) of every sample, for grid_scatter_kernel
+  uint8_t* seg8;  // [N] segment index (255 = no segment)
 };
 
 // D[128,Nin] = G[128,Kout] * W[Kout,Nin]  : A = gradient tile (K-major), B = forward blob read MN-major
@@ -141,6 +144,8 @@ struct ScatterArgs {
   hrf_samples s;
   const hrf_segment_grads* seg_grads;
   const float2* dfeat;  // [16 levels][N] float2, written by field_backward_kernel
+  const float4* pos4;   // [N] (x,y,z,t), written by field_backward_kernel
+  const uint8_t* seg8;  // [N]
 };
 
 __global__ void __launch_bounds__(256, 3) grid_scatter_kernel(const __grid_constant__ ScatterArgs a) {
@@ -188,8 +193,12 @@ __global__ void __launch_bounds__(256, 3) grid_scatter_kernel(const __grid_const
 #pragma unroll 1
   for (int j = 0; j < cnt; ++j) {
     const int64_t i = i0 + j;
-    const Sample s = load_sample(f, a.s, i, false);
-    if (s.seg == nullptr) continue;
+    const uint32_t sgi = a.seg8[i];
+    if (sgi == 255u) continue;
+    const float4 p4 = __ldg(a.pos4 + i);   // (the ray -> position chain was resolved once, in field_backward_kernel)
+    Sample s;
+    s.x = p4.x, s.y = p4.y, s.z = p4.z, s.t = p4.w;
+    s.seg = f.segments + sgi;
     const float2 dO = __ldg(dfl + i);
     const float c0 = (k == 2) ? s.y : s.x;                       // grid coordinates (decomposition4d.py:126-129)
     const float c1 = (k == 0 || k == 1) ? s.y : s.z;
@@ -275,6 +284,10 @@ __global__ void __launch_bounds__(kTile, 2) field_backward_kernel(const __grid_c
     const int64_t i = tile * kTile + tid;
     const bool valid = i < n;
     const Sample s = load_sample(f, args.s, i, true);
+    if (valid) {
+      args.pos4[i] = make_float4(s.x, s.y, s.z, s.t);
+      args.seg8[i] = s.seg != nullptr ? (uint8_t)(s.seg - f.segments) : (uint8_t)255;
+    }
     if (args.feat_in != nullptr) {
 #pragma unroll
       for (int kg = 0; kg < 4; ++kg)
@@ -295,21 +308,9 @@ __global__ void __launch_bounds__(kTile, 2) field_backward_kernel(const __grid_c
     mma_round(sm, phase, [&] { issue_layer(tm + kColWork, a_hs, wbase + kWSig2, 16, 64); });
     tmem_ld16(trow + kColWork, o);
     const float h0 = o[0];
-    {
-      float sh[16];
-      sh4(s.dx, s.dy, s.dz, sh);
-      *reinterpret_cast<uint4*>(sm.cin + 0 * kAChunk + roff) = make_uint4(
-          pack_bf16x2(sh[0], sh[1]), pack_bf16x2(sh[2], sh[3]), pack_bf16x2(sh[4], sh[5]), pack_bf16x2(sh[6], sh[7]));
-      *reinterpret_cast<uint4*>(sm.cin + 1 * kAChunk + roff) =
-          make_uint4(pack_bf16x2(sh[8], sh[9]), pack_bf16x2(sh[10], sh[11]), pack_bf16x2(sh[12], sh[13]),
-                     pack_bf16x2(sh[14], sh[15]));
-      *reinterpret_cast<uint4*>(sm.cin + 2 * kAChunk + roff) = make_uint4(
-          pack_bf16x2(o[1], o[2]), pack_bf16x2(o[3], o[4]), pack_bf16x2(o[5], o[6]), pack_bf16x2(o[7], o[8]));
-      *reinterpret_cast<uint4*>(sm.cin + 3 * kAChunk + roff) =
-          make_uint4(pack_bf16x2(o[9], o[10]), pack_bf16x2(o[11], o[12]), pack_bf16x2(o[13], o[14]),
-                     pack_bf16x2(o[15], 1.0f));
-    }
-    mma_round(sm, phase, [&] { issue_layer(tm + kColWork, a_cin, wbase + kWCol1, 64, 32); });
+    write_color_input(f, sm.cin, roff, s, o);
+    const int K1 = f.color_in_width;
+    mma_round(sm, phase, [&] { issue_layer(tm + kColWork, a_cin, wbase + kWCol1, 64, K1); });
     tmem_ld64(trow + kColWork, v);
     store_relu64(sm.h1, roff, v);
     mma_round(sm, phase, [&] { issue_layer(tm + kColWork, a_h1, wbase + kWCol2, 64, 64); });
@@ -345,12 +346,19 @@ __global__ void __launch_bounds__(kTile, 2) field_backward_kernel(const __grid_c
     tmem_ld64(trow + kColWork, v);
     relu_backward_inplace64(sm.h1, roff, v);
     mma_round(sm, phase, [&] {
-      issue_wgrad(tm + kColW1c, a_h1, a_cin, 32, have_acc);                  // dW1c += dH1^T Cin
-      issue_dgrad(tm + kColWork, a_h1, wbase + kWCol1, 32, 64);              // dCin = dH1 W1c
+      issue_wgrad(tm + kColW1c, a_h1, a_cin, K1, have_acc);                  // dW1c += dH1^T Cin
+      issue_dgrad(tm + kColWork, a_h1, wbase + kWCol1, K1, 64);              // dCin = dH1 W1c
     });
     {
-      float dc[32];
+      float dc[48];
       tmem_ld32(trow + kColWork, dc);
+      if (K1 == 48) tmem_ld16(trow + kColWork + 32, dc + 32);
+      if (args.d_emb != nullptr && s.cam >= 0) {  // d(camera embedding): colour-input features 31..30+E
+        const int E = f.camera_embedding_dim;
+#pragma unroll
+        for (int e = 0; e < HRF_MAX_CAMERA_EMBEDDING_DIM; ++e)
+          if (e < E) atomicAdd(args.d_emb + (size_t)s.cam * E + e, dc[31 + e]);
+      }
       // d(sigma-net output): col 0 from the density (truncated_exp backward, activation.py:21), 1..15 = d geo
       float dh0 = 0.f;
       if (valid && args.d_sigma != nullptr)
@@ -397,15 +405,20 @@ __global__ void __launch_bounds__(kTile, 2) field_backward_kernel(const __grid_c
     tmem_ld16(trow + kColW2s, acc);
     if (lane < 16)
       for (int c = 0; c < 16; ++c) atomicAdd(args.d_mlp + kGSig2 + c * 64 + m, acc[c]);
+    const int K1 = f.color_in_width;
+    const int gcol2 = kGCol1 + 64 * K1, gcol3 = gcol2 + 4096;
     tmem_ld32(trow + kColW1c, acc);
+    if (K1 == 48) tmem_ld16(trow + kColW1c + 32, acc + 32);
     if (lane < 16)
-      for (int c = 0; c < 32; ++c) atomicAdd(args.d_mlp + kGCol1 + m * 32 + c, acc[c]);
+#pragma unroll
+      for (int c = 0; c < 48; ++c)
+        if (c < K1) atomicAdd(args.d_mlp + kGCol1 + m * K1 + c, acc[c]);
     tmem_ld64(trow + kColW2c, acc);
     if (lane < 16)
-      for (int c = 0; c < 64; ++c) atomicAdd(args.d_mlp + kGCol2 + m * 64 + c, acc[c]);
+      for (int c = 0; c < 64; ++c) atomicAdd(args.d_mlp + gcol2 + m * 64 + c, acc[c]);
     tmem_ld16(trow + kColW3c, acc);
     if (lane < 16)
-      for (int c = 0; c < 16; ++c) atomicAdd(args.d_mlp + kGCol3 + c * 64 + m, acc[c]);
+      for (int c = 0; c < 16; ++c) atomicAdd(args.d_mlp + gcol3 + c * 64 + m, acc[c]);
   }
   tc_fence_before();
   __syncthreads();
@@ -418,10 +431,11 @@ using namespace hrf;
 
 extern "C" int hrf_field_backward(const hrf_field* f, const hrf_samples* s, const hrf_segment_grads* seg_grads,
                                   const float* d_sigma, const float* d_rgb, const void* feat_bf16, float* d_mlp,
-                                  void* workspace, void* stream) {
+                                  float* d_camera_embeddings, void* workspace, void* stream) {
   HRF_REQUIRE(f != nullptr && s != nullptr && seg_grads != nullptr, "null argument");
+  HRF_REQUIRE(f->num_segments < 255, "at most 254 temporal segments");
   if (s->num_samples == 0) return 0;
-  HRF_REQUIRE(workspace != nullptr, "hrf_field_backward needs a workspace of 128 bytes per sample");
+  HRF_REQUIRE(workspace != nullptr, "hrf_field_backward needs a workspace of 160 bytes per sample");
   HRF_REQUIRE(d_sigma != nullptr || d_rgb != nullptr, "no upstream gradient given");
   if (s->ray_origins == nullptr) {
     HRF_REQUIRE(s->positions && s->frame_numbers, "query form needs positions and frame numbers");
@@ -436,7 +450,10 @@ extern "C" int hrf_field_backward(const hrf_field* f, const hrf_samples* s, cons
   a.d_rgb = d_rgb;
   a.feat_in = reinterpret_cast<const uint4*>(feat_bf16);
   a.d_mlp = d_mlp;
+  a.d_emb = d_camera_embeddings;
   a.dfeat = reinterpret_cast<float2*>(workspace);
+  a.pos4 = reinterpret_cast<float4*>(reinterpret_cast<char*>(workspace) + 128 * (size_t)s->num_samples);
+  a.seg8 = reinterpret_cast<uint8_t*>(reinterpret_cast<char*>(workspace) + 144 * (size_t)s->num_samples);
   const int64_t tiles = (s->num_samples + kTile - 1) / kTile;
   const int smem = (int)sizeof(BwdSmem) + 1024;
   const int64_t max_ctas = (int64_t)sm_count() * 2;
@@ -450,6 +467,8 @@ extern "C" int hrf_field_backward(const hrf_field* f, const hrf_samples* s, cons
   sa.s = *s;
   sa.seg_grads = seg_grads;
   sa.dfeat = a.dfeat;
+  sa.pos4 = a.pos4;
+  sa.seg8 = a.seg8;
   {
     const int64_t chunks = (s->num_samples + kChunk - 1) / kChunk;
     grid_scatter_kernel<<<dim3((unsigned)((chunks + 255) / 256), HRF_N_LEVELS * 4), 256, 0, st>>>(sa);

@@ -14,12 +14,12 @@ constexpr uint32_t kPrimeZ = 805459861u;
 // element (n,k) of W[N,K] at ((k/8)*(N/8) + n/8)*128 + (n%8)*16 + (k%8)*2).
 constexpr uint32_t kWSig1 = 0;       // sigma  W1 [64,32]
 constexpr uint32_t kWSig2 = 4096;    // sigma  W2 [16,64]
-constexpr uint32_t kWCol1 = 6144;    // colour W1 [64,32]
-constexpr uint32_t kWCol2 = 10240;   // colour W2 [64,64]
-constexpr uint32_t kWCol3 = 18432;   // colour W3 [16,64]
+constexpr uint32_t kWCol1 = 6144;    // colour W1 [64,32] or [64,48] (room for 48: the k-chunk stride does not depend on K)
+constexpr uint32_t kWCol2 = 12288;   // colour W2 [64,64]
+constexpr uint32_t kWCol3 = 20480;   // colour W3 [16,64]
 constexpr uint32_t kWBlobBytes = HRF_MLP_BLOB_BYTES;
 // row-major fp32 gradient buffer offsets (elements)
-constexpr int kGSig1 = 0, kGSig2 = 2048, kGCol1 = 3072, kGCol2 = 5120, kGCol3 = 9216, kGTotal = 10240;
+constexpr int kGSig1 = 0, kGSig2 = 2048, kGCol1 = 3072;  // colour W2 at 3072 + 64*K, colour W3 4096 later (K = 32 | 48)
 
 // A-operand tile: 128 rows x K bf16, K-major SWIZZLE_NONE: element (r,k) at
 // (k/8)*kAChunk + (r/8)*128 + (r%8)*16 + (k%8)*2   -> LBO = kAChunk (K direction), SBO = 128 (M direction).
@@ -55,6 +55,7 @@ struct Sample {
   float x, y, z, t;        // normalised coordinates in [0,1] (positions + 0.5, local time)
   float dx, dy, dz;        // view direction
   const hrf_segment* seg;  // segment descriptor (NULL for padding threads)
+  int cam;                 // camera row of the embedding table, or -1 (zeros: evaluation / no embedding)
 };
 
 __device__ __forceinline__ Sample load_sample(const hrf_field& f, const hrf_samples& s, int64_t i, bool need_dir) {
@@ -62,7 +63,9 @@ __device__ __forceinline__ Sample load_sample(const hrf_field& f, const hrf_samp
   o.seg = nullptr;
   o.x = o.y = o.z = o.t = 0.f;
   o.dx = o.dy = o.dz = 0.f;
+  o.cam = -1;
   if (i >= s.num_samples) return o;
+  const bool want_cam = need_dir && s.use_camera_embeddings && f.camera_embeddings != nullptr;
   int frame;
   float px, py, pz;
   if (s.ray_origins != nullptr) {
@@ -76,13 +79,16 @@ __device__ __forceinline__ Sample load_sample(const hrf_field& f, const hrf_samp
     py = __fadd_rn(__ldg(ro + 1), __fmul_rn(t, o.dy));
     pz = __fadd_rn(__ldg(ro + 2), __fmul_rn(t, o.dz));
     frame = __ldg(s.ray_frame_numbers + r);
+    if (want_cam && s.ray_camera_numbers != nullptr) o.cam = __ldg(s.ray_camera_numbers + r);
   } else {
     px = __ldg(s.positions + 3 * i), py = __ldg(s.positions + 3 * i + 1), pz = __ldg(s.positions + 3 * i + 2);
     if (need_dir && s.directions != nullptr) {
       o.dx = __ldg(s.directions + 3 * i), o.dy = __ldg(s.directions + 3 * i + 1), o.dz = __ldg(s.directions + 3 * i + 2);
     }
     frame = __ldg(s.frame_numbers + i);
+    if (want_cam && s.camera_numbers != nullptr) o.cam = __ldg(s.camera_numbers + i);
   }
+  if (o.cam < 0 || o.cam >= f.num_cameras) o.cam = -1;
   // humanrf.py:175 : positions + 0.5 ; :176 normalised local frame number
   o.x = __fadd_rn(px, 0.5f), o.y = __fadd_rn(py, 0.5f), o.z = __fadd_rn(pz, 0.5f);
   int sg = -1;
@@ -203,6 +209,36 @@ __device__ __forceinline__ void sh4(float dx, float dy, float dz, float* o) {
   o[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2);
   o[14] = 1.4453057213202769f * z * (x2 - y2);
   o[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
+}
+
+// Colour-net input row (humanrf.py:192-206 + tcnn Composite[SH(4) on 3 dims, Identity] padded with 1.0):
+// [SH 0..15 | geo 16..30 | camera embedding 31..30+E | 1.0 ...] as bf16, K = 32 (E = 0) or 48.
+__device__ __forceinline__ void write_color_input(const hrf_field& f, unsigned char* abuf, uint32_t roff, const Sample& s,
+                                                  const float* o /* sigma-net output, o[1..15] = geo */) {
+  float sh[16];
+  sh4(s.dx, s.dy, s.dz, sh);
+  const int E = f.camera_embedding_dim;
+  const float* emb = (s.cam >= 0) ? f.camera_embeddings + (size_t)s.cam * E : nullptr;
+  auto tail = [&](int j) -> float {  // feature j >= 31
+    const int e = j - 31;
+    return e < E ? (emb != nullptr ? __ldg(emb + e) : 0.f) : 1.0f;
+  };
+  *reinterpret_cast<uint4*>(abuf + 0 * kAChunk + roff) = make_uint4(
+      pack_bf16x2(sh[0], sh[1]), pack_bf16x2(sh[2], sh[3]), pack_bf16x2(sh[4], sh[5]), pack_bf16x2(sh[6], sh[7]));
+  *reinterpret_cast<uint4*>(abuf + 1 * kAChunk + roff) = make_uint4(
+      pack_bf16x2(sh[8], sh[9]), pack_bf16x2(sh[10], sh[11]), pack_bf16x2(sh[12], sh[13]), pack_bf16x2(sh[14], sh[15]));
+  *reinterpret_cast<uint4*>(abuf + 2 * kAChunk + roff) = make_uint4(
+      pack_bf16x2(o[1], o[2]), pack_bf16x2(o[3], o[4]), pack_bf16x2(o[5], o[6]), pack_bf16x2(o[7], o[8]));
+  *reinterpret_cast<uint4*>(abuf + 3 * kAChunk + roff) = make_uint4(
+      pack_bf16x2(o[9], o[10]), pack_bf16x2(o[11], o[12]), pack_bf16x2(o[13], o[14]), pack_bf16x2(o[15], tail(31)));
+  if (f.color_in_width == 48) {
+    *reinterpret_cast<uint4*>(abuf + 4 * kAChunk + roff) = make_uint4(
+        pack_bf16x2(tail(32), tail(33)), pack_bf16x2(tail(34), tail(35)), pack_bf16x2(tail(36), tail(37)),
+        pack_bf16x2(tail(38), tail(39)));
+    *reinterpret_cast<uint4*>(abuf + 5 * kAChunk + roff) = make_uint4(
+        pack_bf16x2(tail(40), tail(41)), pack_bf16x2(tail(42), tail(43)), pack_bf16x2(tail(44), tail(45)),
+        pack_bf16x2(tail(46), tail(47)));
+  }
 }
 
 // Encode one sample (4 grids x 16 levels, composed with the vector lerps) and write the 32

@@ -214,22 +214,9 @@ __global__ void __launch_bounds__(kTile, kCtasPerSm) field_forward_kernel(const 
     if (args.mode == 0) continue;
 
     // ---- colour net: [SH16 | geo15 | 1.0] -> 64 (ReLU) -> 64 (ReLU) -> 16 -> sigmoid[:3] ----
-    {
-      float sh[16];
-      sh4(s.dx, s.dy, s.dz, sh);
-      const uint32_t roff = a_row_off(tid);
-      *reinterpret_cast<uint4*>(sm.a + 0 * kAChunk + roff) = make_uint4(
-          pack_bf16x2(sh[0], sh[1]), pack_bf16x2(sh[2], sh[3]), pack_bf16x2(sh[4], sh[5]), pack_bf16x2(sh[6], sh[7]));
-      *reinterpret_cast<uint4*>(sm.a + 1 * kAChunk + roff) =
-          make_uint4(pack_bf16x2(sh[8], sh[9]), pack_bf16x2(sh[10], sh[11]), pack_bf16x2(sh[12], sh[13]),
-                     pack_bf16x2(sh[14], sh[15]));
-      *reinterpret_cast<uint4*>(sm.a + 2 * kAChunk + roff) = make_uint4(
-          pack_bf16x2(o[1], o[2]), pack_bf16x2(o[3], o[4]), pack_bf16x2(o[5], o[6]), pack_bf16x2(o[7], o[8]));
-      *reinterpret_cast<uint4*>(sm.a + 3 * kAChunk + roff) =
-          make_uint4(pack_bf16x2(o[9], o[10]), pack_bf16x2(o[11], o[12]), pack_bf16x2(o[13], o[14]),
-                     pack_bf16x2(o[15], 1.0f));
-    }
-    run_layer<kSimt, 64, 32>(sm, sm.a, kWCol1, phase, v);
+    write_color_input(f, sm.a, a_row_off(tid), s, o);
+    if (f.color_in_width == 48) run_layer<kSimt, 64, 48>(sm, sm.a, kWCol1, phase, v);
+    else run_layer<kSimt, 64, 32>(sm, sm.a, kWCol1, phase, v);
     store_hidden(sm.a, tid, v);
     run_layer<kSimt, 64, 64>(sm, sm.a, kWCol2, phase, v);
     store_hidden(sm.a, tid, v);
@@ -287,6 +274,9 @@ static int check_field_args(const hrf_field* f, const hrf_samples* s, int mode) 
   HRF_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (density) or 1 (density+radiance)");
   HRF_REQUIRE(s->num_samples >= 0, "negative sample count");
   HRF_REQUIRE(f->mlp_blob != nullptr && f->segments != nullptr, "field not initialised");
+  HRF_REQUIRE(f->color_in_width == 32 || f->color_in_width == 48, "color_in_width must be 32 or 48");
+  HRF_REQUIRE(f->camera_embedding_dim >= 0 && 31 + f->camera_embedding_dim <= f->color_in_width,
+              "camera embedding does not fit the colour-net input width");
   if (s->num_samples == 0) return 0;
   if (s->ray_origins != nullptr) {
     HRF_REQUIRE(s->ray_directions && s->ray_frame_numbers && s->sample_distances && s->ray_indices,

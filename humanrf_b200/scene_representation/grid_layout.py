@@ -49,20 +49,37 @@ class GridLayout:
 
 
 # ---- packed bf16 MLP blob (UMMA K-major SWIZZLE_NONE core-matrix layout, csrc/field_common.cuh) ----
-MLP_LAYERS = (("sigma", 64, 32), ("sigma", 16, 64), ("color", 64, 32), ("color", 64, 64), ("color", 16, 64))
 MLP_SIGMA_PARAMS = 64 * 32 + 16 * 64          # 3072  (tcnn FullyFusedMLP, output padded to 16)
-MLP_COLOR_PARAMS = 64 * 32 + 64 * 64 + 16 * 64  # 7168
+MLP_BLOB_ELEMS = 22528 // 2
+# byte offsets of the five weight matrices inside the blob (kWSig1.. in csrc/field_common.cuh)
+_BLOB_OFFSETS = (0, 4096, 6144, 12288, 20480)
 
 
-def mlp_blob_permutation() -> np.ndarray:
-    """perm such that blob_elems = cat(sigma_params, color_params)[perm]  (10240 bf16 elements)."""
-    perm = np.zeros(10240, np.int64)
-    src = 0
-    dst = 0
-    for _, n_out, n_in in MLP_LAYERS:
+def color_in_width(camera_embedding_dim: int) -> int:
+    """tcnn Composite[SH(16) | Identity(15 + E)] padded to a multiple of 16 with 1.0 (humanrf.py:135-156)."""
+    return 32 if camera_embedding_dim == 0 else 48
+
+
+def mlp_layers(camera_embedding_dim: int = 0):
+    k = color_in_width(camera_embedding_dim)
+    return ((64, 32), (16, 64), (64, k), (64, 64), (16, 64))
+
+
+def mlp_color_params(camera_embedding_dim: int = 0) -> int:
+    return sum(o * i for o, i in mlp_layers(camera_embedding_dim)[2:])
+
+
+MLP_COLOR_PARAMS = mlp_color_params(0)  # 7168
+
+
+def mlp_blob_permutation(camera_embedding_dim: int = 0):
+    """(dst, src): blob_elems[dst] = cat(sigma_params, color_params)[src]; untouched blob elements stay 0."""
+    dst, src = [], []
+    s0 = 0
+    for (n_out, n_in), off in zip(mlp_layers(camera_embedding_dim), _BLOB_OFFSETS):
         n, k = np.meshgrid(np.arange(n_out), np.arange(n_in), indexing="ij")
-        off = ((k // 8) * (n_out // 8) + n // 8) * 64 + (n % 8) * 8 + (k % 8)
-        perm[dst + off.reshape(-1)] = src + (n * n_in + k).reshape(-1)
-        src += n_out * n_in
-        dst += n_out * n_in
-    return perm
+        d = off // 2 + ((k // 8) * (n_out // 8) + n // 8) * 64 + (n % 8) * 8 + (k % 8)
+        dst.append(d.reshape(-1))
+        src.append(s0 + (n * n_in + k).reshape(-1))
+        s0 += n_out * n_in
+    return np.concatenate(dst).astype(np.int64), np.concatenate(src).astype(np.int64)

@@ -23,8 +23,8 @@ import numpy as np
 import torch
 
 from .. import _lib as L
-from .grid_layout import (MLP_COLOR_PARAMS, MLP_SIGMA_PARAMS, GridLayout, mlp_blob_permutation,
-                          segment_log2_hashmap_size)
+from .grid_layout import (MLP_BLOB_ELEMS, MLP_SIGMA_PARAMS, GridLayout, color_in_width, mlp_blob_permutation,
+                          mlp_color_params, mlp_layers, segment_log2_hashmap_size)
 from .query_io import QueryInput, QueryOutput
 
 GRID_NAMES = ("xyz_encoding", "xyt_encoding", "yzt_encoding", "xzt_encoding")  # decomposition4d.py:126-129
@@ -76,12 +76,14 @@ class HumanRF(torch.nn.Module):
             raise NotImplementedError(
                 "the fused sm_100a kernel is specialised for the reference defaults (model_args.py:10-19): "
                 "n_neurons=64, geometry_feature_dim=15, 1/2 hidden layers, sh_degree=4")
-        if camera_embedding_dim != 0:
-            raise NotImplementedError("camera_embedding_dim > 0 is not implemented yet (paper setting is 0)")
+        if not 0 <= camera_embedding_dim <= 17:
+            raise NotImplementedError("camera_embedding_dim must be in [0, 17] (16 SH + 15 geometry + E <= 48 inputs)")
         self.density_scale = float(density_scale)
         self.num_frames = len(sorted_frame_numbers)
         self.num_segments = len(segment_sizes)
         self.camera_embedding_dim = camera_embedding_dim
+        if camera_embedding_dim > 0:
+            self.camera_embeddings = torch.nn.Embedding(160, camera_embedding_dim)  # humanrf.py:75-76
 
         # humanrf.py:79-103
         end = np.cumsum(segment_sizes, dtype=np.int32)
@@ -105,36 +107,51 @@ class HumanRF(torch.nn.Module):
                 ngp_base_resolution=coarsest_resolution, ngp_finest_resolution=finest_resolution,
                 vectors_finest_resolution=finest_resolution))
         self.total_feature_dim = n_levels * n_features_per_level
-        self.sigma_net = _FlatParams(_xavier_flat([(64, 32), (16, 64)]))
-        self.color_net = _FlatParams(_xavier_flat([(64, 32), (64, 64), (16, 64)]))
-        assert self.sigma_net.params.numel() == MLP_SIGMA_PARAMS and self.color_net.params.numel() == MLP_COLOR_PARAMS
+        layers = mlp_layers(camera_embedding_dim)
+        self.sigma_net = _FlatParams(_xavier_flat(layers[:2]))
+        self.color_net = _FlatParams(_xavier_flat(layers[2:]))
+        assert self.sigma_net.params.numel() == MLP_SIGMA_PARAMS
+        assert self.color_net.params.numel() == mlp_color_params(camera_embedding_dim)
         self._native: Optional[_NativeField] = None
 
     # ------------------------------------------------------------------ reference API
     def density(self, query_input: QueryInput) -> QueryOutput:
-        sigma, geo, _ = _FieldFunction.apply(self, 0, query_input.positions, None, query_input.frame_numbers,
+        sigma, geo, _ = _FieldFunction.apply(self, 0, query_input.positions, None, query_input.frame_numbers, None,
                                              *self.hot_parameters())
         return QueryOutput(density=sigma, geometry_features=geo)
 
     def forward(self, query_input: QueryInput) -> QueryOutput:
+        # humanrf.py:194-204: the camera embedding is looked up while training and is all zeros otherwise
+        cams = query_input.camera_numbers if (self.camera_embedding_dim > 0 and query_input.is_training) else None
         sigma, geo, rgb = _FieldFunction.apply(self, 1, query_input.positions, query_input.directions,
-                                               query_input.frame_numbers, *self.hot_parameters())
+                                               query_input.frame_numbers, cams, *self.hot_parameters())
         return QueryOutput(density=sigma, geometry_features=geo, radiance=rgb)
 
     def get_params(self, lr):
-        return [
+        params = [
             {'params': self.feature_grids.parameters(), 'lr': lr},
             {'params': self.sigma_net.parameters(), 'lr': lr},
             {'params': self.color_net.parameters(), 'lr': lr},
         ]
+        if self.camera_embedding_dim > 0:
+            params.append({'params': self.camera_embeddings.parameters(), 'lr': lr})
+        return params
 
     # ------------------------------------------------------------------ native plumbing
     def hot_parameters(self) -> List[torch.nn.Parameter]:
-        """Per segment: 4 grids + vectors; then sigma and colour MLP parameters (gradient order)."""
+        """Per segment: 4 grids + vectors; then sigma and colour MLP parameters; then the camera embedding table
+        if there is one (gradient order)."""
         ps: List[torch.nn.Parameter] = []
         for fg in self.feature_grids:
             ps += fg.grids() + [fg.vectors]
-        return ps + [self.sigma_net.params, self.color_net.params]
+        ps += [self.sigma_net.params, self.color_net.params]
+        if self.camera_embedding_dim > 0:
+            ps.append(self.camera_embeddings.weight)
+        return ps
+
+    @property
+    def mlp_grad_elems(self) -> int:
+        return MLP_SIGMA_PARAMS + mlp_color_params(self.camera_embedding_dim)
 
     def native(self) -> "_NativeField":
         if self._native is None:
@@ -177,8 +194,9 @@ class _NativeField:
             self.shadows = []
             for fg in m.feature_grids:
                 self.shadows.append([torch.empty(g.numel(), dtype=torch.bfloat16, device=dev) for g in fg.grids()])
-            self.blob = torch.empty(L.MLP_BLOB_BYTES // 2, dtype=torch.bfloat16, device=dev)
-            self.perm = torch.from_numpy(mlp_blob_permutation()).to(dev)
+            self.blob = torch.zeros(MLP_BLOB_ELEMS, dtype=torch.bfloat16, device=dev)
+            dst, src = mlp_blob_permutation(m.camera_embedding_dim)
+            self.perm = (torch.from_numpy(dst).to(dev), torch.from_numpy(src).to(dev))
             segs = (L.Segment * m.num_segments)()
             for s, fg in enumerate(m.feature_grids):
                 lay = fg.layout
@@ -205,6 +223,13 @@ class _NativeField:
             f.lut_size = m.frame_numbers_to_segment_numbers.numel()
             f.vec_res = m.feature_grids[0].vectors.shape[1]
             f.density_scale = m.density_scale
+            f.camera_embedding_dim = m.camera_embedding_dim
+            f.color_in_width = color_in_width(m.camera_embedding_dim)
+            if m.camera_embedding_dim > 0:
+                f.camera_embeddings = m.camera_embeddings.weight.data_ptr()
+                f.num_cameras = m.camera_embeddings.weight.shape[0]
+            else:
+                f.camera_embeddings, f.num_cameras = None, 0
             self.keys = keys
             self.versions = None
         versions = tuple(p._version for p in params)
@@ -218,26 +243,38 @@ class _NativeField:
                             L.check(lib.hrf_cast_bf16(g.data_ptr(), self.shadows[s][k].data_ptr(), g.numel(), L.stream()))
                         i += 1
                     i += 1  # vectors are read as fp32 directly
-                if old is None or old[-2:] != versions[-2:]:
-                    flat = torch.cat((m.sigma_net.params.detach(), m.color_net.params.detach()))
-                    self.blob.copy_(flat[self.perm].to(torch.bfloat16))
+                if old is None or old[self.n_table_params:] != versions[self.n_table_params:]:
+                    self.repack_mlp()
             self.versions = versions
+
+    @property
+    def n_table_params(self) -> int:
+        return 5 * self.model.num_segments
+
+    def repack_mlp(self) -> None:
+        m = self.model
+        flat = torch.cat((m.sigma_net.params.detach(), m.color_net.params.detach()))
+        self.blob[self.perm[0]] = flat[self.perm[1]].to(torch.bfloat16)
 
     def mark_shadows_current(self) -> None:
         """Called by the fused optimiser, which writes the shadows itself."""
         self.versions = tuple(p._version for p in self.model.hot_parameters())
 
     # -------------------------------------------------------------------------------------
-    def samples_query(self, positions, directions, frame_numbers) -> L.Samples:
+    def samples_query(self, positions, directions, frame_numbers, camera_numbers=None) -> L.Samples:
         s = L.Samples()
         s.positions = positions.data_ptr()
         s.directions = None if directions is None else directions.data_ptr()
         s.frame_numbers = frame_numbers.data_ptr()
         s.num_samples = positions.shape[0]
-        s._keep = (positions, directions, frame_numbers)   # the struct holds raw pointers: keep the tensors alive
+        if camera_numbers is not None:
+            s.camera_numbers = camera_numbers.data_ptr()
+            s.use_camera_embeddings = 1
+        s._keep = (positions, directions, frame_numbers, camera_numbers)   # raw pointers inside: keep the tensors alive
         return s
 
-    def samples_rays(self, ray_origins, ray_directions, ray_frames, distances, ray_indices) -> L.Samples:
+    def samples_rays(self, ray_origins, ray_directions, ray_frames, distances, ray_indices,
+                     ray_cameras=None) -> L.Samples:
         s = L.Samples()
         s.ray_origins = ray_origins.data_ptr()
         s.ray_directions = ray_directions.data_ptr()
@@ -245,7 +282,10 @@ class _NativeField:
         s.sample_distances = distances.data_ptr()
         s.ray_indices = ray_indices.data_ptr()
         s.num_samples = distances.shape[0]
-        s._keep = (ray_origins, ray_directions, ray_frames, distances, ray_indices)
+        if ray_cameras is not None:
+            s.ray_camera_numbers = ray_cameras.data_ptr()
+            s.use_camera_embeddings = 1
+        s._keep = (ray_origins, ray_directions, ray_frames, distances, ray_indices, ray_cameras)
         return s
 
     def forward(self, samples: L.Samples, mode: int, want_geo: bool, want_feat: bool, mlp_impl: int = 0):
@@ -285,10 +325,12 @@ class _NativeField:
             sg[s].vectors = grad_tensors[i].data_ptr()
             i += 1
         sg_dev = torch.from_numpy(np.frombuffer(bytes(sg), dtype=np.uint8).copy()).to(dev)
-        d_mlp = torch.zeros(L.MLP_GRAD_ELEMS, dtype=torch.float32, device=dev)
-        ws = torch.empty(int(samples.num_samples) * 32, dtype=torch.float32, device=dev)
+        d_mlp = torch.zeros(m.mlp_grad_elems, dtype=torch.float32, device=dev)
+        d_emb = grad_tensors[i + 2] if m.camera_embedding_dim > 0 else None
+        ws = torch.empty(int(samples.num_samples) * 40, dtype=torch.float32, device=dev)   # 160 B / sample
         L.check(L.lib().hrf_field_backward(C.byref(self.field), C.byref(samples), sg_dev.data_ptr(), L.ptr(d_sigma),
-                                           L.ptr(d_rgb), L.ptr(feat), d_mlp.data_ptr(), ws.data_ptr(), L.stream()))
+                                           L.ptr(d_rgb), L.ptr(feat), d_mlp.data_ptr(), L.ptr(d_emb), ws.data_ptr(),
+                                           L.stream()))
         grad_tensors[i].add_(d_mlp[:MLP_SIGMA_PARAMS])
         grad_tensors[i + 1].add_(d_mlp[MLP_SIGMA_PARAMS:])
         return sg_dev  # keep alive until the kernel has run (stream-ordered free is safe, but be explicit)
@@ -306,17 +348,19 @@ class _FieldFunction(torch.autograd.Function):
     """autograd wrapper of the fused kernels in QueryInput form (humanrf.py:158-208)."""
 
     @staticmethod
-    def forward(ctx, model: HumanRF, mode: int, positions, directions, frame_numbers, *params):
+    def forward(ctx, model: HumanRF, mode: int, positions, directions, frame_numbers, camera_numbers, *params):
         nat = model.native()
         pos = L.require_cuda(_as_f32c(positions), "positions")
         dirs = None if directions is None else L.require_cuda(_as_f32c(directions), "directions")
         frames = L.require_cuda(_as_frames(frame_numbers), "frame_numbers")
-        needs_grad = any(ctx.needs_input_grad[5:])
-        samples = nat.samples_query(pos, dirs, frames)
+        cams = None if camera_numbers is None else L.require_cuda(_as_frames(camera_numbers), "camera_numbers")
+        needs_grad = any(ctx.needs_input_grad[6:])
+        samples = nat.samples_query(pos, dirs, frames, cams)
         sigma, geo, rgb, feat = nat.forward(samples, mode, want_geo=True, want_feat=needs_grad)
         ctx.model, ctx.mode = model, mode
-        ctx.save_for_backward(pos, dirs if dirs is not None else pos, frames, feat if feat is not None else pos)
-        ctx.has_dirs = dirs is not None
+        ctx.save_for_backward(pos, dirs if dirs is not None else pos, frames, feat if feat is not None else pos,
+                              cams if cams is not None else frames)
+        ctx.has_dirs, ctx.has_cams = dirs is not None, cams is not None
         geo_out = geo[:, 1:]
         ctx.mark_non_differentiable(geo_out)
         if rgb is None:
@@ -327,15 +371,15 @@ class _FieldFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, d_sigma, d_geo, d_rgb):
         model = ctx.model
-        pos, dirs, frames, feat = ctx.saved_tensors
+        pos, dirs, frames, feat, cams = ctx.saved_tensors
         nat = model.native()
         params = model.hot_parameters()
         grads = [torch.zeros_like(p) for p in params]
-        samples = nat.samples_query(pos, dirs if ctx.has_dirs else None, frames)
+        samples = nat.samples_query(pos, dirs if ctx.has_dirs else None, frames, cams if ctx.has_cams else None)
         ds = None if d_sigma is None else _as_f32c(d_sigma)
         dr = None if (d_rgb is None or ctx.mode == 0) else _as_f32c(d_rgb)
         if ds is None:
             ds = torch.zeros(pos.shape[0], dtype=torch.float32, device=pos.device)
         keep = nat.backward(samples, ds, dr, feat, grads)
         del keep
-        return (None, None, None, None, None, *grads)
+        return (None, None, None, None, None, None, *grads)

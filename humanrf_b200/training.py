@@ -57,8 +57,9 @@ class FusedTrainer:
             sg[s].vectors = self.grad_views[i].data_ptr()
             i += 1
         self.sg_dev = torch.from_numpy(np.frombuffer(bytes(sg), dtype=np.uint8).copy()).to(dev)
-        self.mlp_grad = self.grad[self.offsets[i]:]            # sigma params then colour params: contiguous 10240
-        assert self.mlp_grad.numel() == L.MLP_GRAD_ELEMS
+        self.mlp_grad = self.grad[self.offsets[i]:self.offsets[i + 2]]   # sigma params then colour params, contiguous
+        assert self.mlp_grad.numel() == model.mlp_grad_elems
+        self.emb_grad = self.grad[self.offsets[i + 2]:] if model.camera_embedding_dim > 0 else None
         self.last = {}
         self.profile = False
 
@@ -67,7 +68,7 @@ class FusedTrainer:
         return self.lr * self.lr_decay ** min(self.t / self.max_steps, 1.0)  # run.py:102-104
 
     def step(self, o, d, frames, t, ri, rgba, num_rays: int, kernel_event=None, return_loss: bool = False,
-             background: Optional[torch.Tensor] = None):
+             background: Optional[torch.Tensor] = None, cameras: Optional[torch.Tensor] = None):
         """One optimisation step on a ray batch given in InputBatch layout (device tensors).
         Returns the number of kernels launched, or the loss value when return_loss."""
         lib, nat, dev = L.lib(), self.model.native(), t.device
@@ -105,7 +106,7 @@ class FusedTrainer:
             off = kept_off                                   # hrf_prune's scan IS the ray-offset table of the survivors
         n = t.shape[0]
         # ---- forward: fused field + compositing
-        samples = nat.samples_rays(o, d, frames, t, ri)
+        samples = nat.samples_rays(o, d, frames, t, ri, cameras if self.model.camera_embedding_dim > 0 else None)
         sigma, _, rgb, feat = nat.forward(samples, 1, want_geo=False, want_feat=True)
         if kernel_event is not None:
             kernel_event.record()
@@ -136,10 +137,10 @@ class FusedTrainer:
                                            bg.data_ptr(), color.grad.data_ptr(), wsum.grad.reshape(-1).data_ptr(),
                                            d_sigma.data_ptr(), d_rgb.data_ptr(), L.stream()))
         self.grad.zero_()
-        ws = torch.empty(n * 32, dtype=torch.float32, device=dev)
+        ws = torch.empty(n * 40, dtype=torch.float32, device=dev)   # 160 B / sample
         L.check(lib.hrf_field_backward(C.byref(nat.field), C.byref(samples), self.sg_dev.data_ptr(), d_sigma.data_ptr(),
-                                       d_rgb.data_ptr(), feat.data_ptr(), self.mlp_grad.data_ptr(), ws.data_ptr(),
-                                       L.stream()))
+                                       d_rgb.data_ptr(), feat.data_ptr(), self.mlp_grad.data_ptr(), L.ptr(self.emb_grad),
+                                       ws.data_ptr(), L.stream()))
         launches += 8 + 12
         mark("backward")
         # ---- data parallel: one all-reduce of the flat bucket (sum), mean over ranks folded into Adam's grad_scale
@@ -169,11 +170,9 @@ class FusedTrainer:
                     i += 1
                 self._adam(i, None, lr, grad_scale)
                 i += 1
-            self._adam(i, None, lr, grad_scale)
-            self._adam(i + 1, None, lr, grad_scale)
-            m = self.model
-            flat = torch.cat((m.sigma_net.params.detach(), m.color_net.params.detach()))
-            nat.blob.copy_(flat[nat.perm].to(torch.bfloat16))
+            for j in range(i, len(self.params)):          # sigma net, colour net, [camera embeddings]
+                self._adam(j, None, lr, grad_scale)
+            nat.repack_mlp()
 
     def _adam(self, i: int, shadow: Optional[torch.Tensor], lr: float, grad_scale: float) -> None:
         p = self.params[i]

@@ -87,11 +87,11 @@ class _RenderFunction(torch.autograd.Function):
     """field forward (ray-batch form) + compositing; backward = composite bwd + fused field bwd."""
 
     @staticmethod
-    def forward(ctx, model: HumanRF, o, d, fr, t, ri, num_rays, background, step, *params):
+    def forward(ctx, model: HumanRF, o, d, fr, t, ri, num_rays, background, step, cams, *params):
         nat = model.native()
         dev = t.device
-        needs_grad = any(ctx.needs_input_grad[9:])
-        samples = nat.samples_rays(o, d, fr, t, ri)
+        needs_grad = any(ctx.needs_input_grad[10:])
+        samples = nat.samples_rays(o, d, fr, t, ri, cams)
         sigma, _, rgb, feat = nat.forward(samples, 1, want_geo=False, want_feat=needs_grad)
         off = ray_offsets(ri, num_rays)
         color = torch.empty((num_rays, 3), dtype=torch.float32, device=dev)
@@ -105,13 +105,15 @@ class _RenderFunction(torch.autograd.Function):
                                               L.stream()))
         ctx.model, ctx.num_rays, ctx.step = model, num_rays, float(step)
         ctx.bg = bg
-        ctx.save_for_backward(o, d, fr, t, ri, sigma, rgb, off, feat if feat is not None else t)
+        ctx.save_for_backward(o, d, fr, t, ri, sigma, rgb, off, feat if feat is not None else t,
+                              cams if cams is not None else fr)
+        ctx.has_cams = cams is not None
         return color, wsum
 
     @staticmethod
     def backward(ctx, d_color, d_wsum):
         model = ctx.model
-        o, d, fr, t, ri, sigma, rgb, off, feat = ctx.saved_tensors
+        o, d, fr, t, ri, sigma, rgb, off, feat, cams = ctx.saved_tensors
         nat = model.native()
         dev = t.device
         n = t.shape[0]
@@ -124,8 +126,8 @@ class _RenderFunction(torch.autograd.Function):
                                                d_sigma.data_ptr(), d_rgb.data_ptr(), L.stream()))
         params = model.hot_parameters()
         grads = [torch.zeros_like(p) for p in params]
-        nat.backward(nat.samples_rays(o, d, fr, t, ri), d_sigma, d_rgb, feat, grads)
-        return (None,) * 9 + tuple(grads)
+        nat.backward(nat.samples_rays(o, d, fr, t, ri, cams if ctx.has_cams else None), d_sigma, d_rgb, feat, grads)
+        return (None,) * 10 + tuple(grads)
 
 
 def render(input_batch: InputBatch, scene_representation: HumanRF, background_rgb: torch.Tensor, is_training: bool,
@@ -133,6 +135,9 @@ def render(input_batch: InputBatch, scene_representation: HumanRF, background_rg
     """volume_rendering.py:87-150.  color = sum w*rgb + background*(1 - sum w); weights_sum = sum w."""
     ib = input_batch
     o, d, fr, t, ri = _ray_arrays(ib)
+    cams = None
+    if scene_representation.camera_embedding_dim > 0 and is_training:   # humanrf.py:194-204 (zeros at evaluation)
+        cams = L.require_cuda(ib.camera_numbers.detach().reshape(-1).to(torch.int32).contiguous(), "camera_numbers")
     color, wsum = _RenderFunction.apply(scene_representation, o, d, fr, t, ri, ib.num_rays, background_rgb,
-                                        render_step_size, *scene_representation.hot_parameters())
+                                        render_step_size, cams, *scene_representation.hot_parameters())
     return RenderOutput(color=color, weights_sum=wsum)

@@ -24,7 +24,8 @@ extern "C" {
 #define HRF_N_FEATURES 32      /* n_levels * n_features_per_level (2)               */
 #define HRF_MLP_WIDTH 64       /* model_args.py:12 n_neurons                        */
 #define HRF_GEO_DIM 15         /* model_args.py:10 geometry_feature_dim             */
-#define HRF_MLP_BLOB_BYTES 20480 /* packed bf16 weights: sigma 64x32,16x64; colour 64x32,64x64,16x64 */
+#define HRF_MLP_BLOB_BYTES 22528 /* packed bf16 weights: sigma 64x32,16x64; colour 64x(32|48),64x64,16x64 */
+#define HRF_MAX_CAMERA_EMBEDDING_DIM 17 /* 16 SH + 15 geo + E <= 48 */
 
 const char* hrf_last_error(void);
 int hrf_version(void);
@@ -116,6 +117,10 @@ typedef struct {
   uint32_t level_res[HRF_N_LEVELS];
   int32_t  num_segments, lut_size, vec_res;
   float    density_scale;
+  /* camera embeddings (humanrf.py:75-76,194-204): fp32 [num_cameras, camera_embedding_dim], or NULL / 0 */
+  const float* camera_embeddings;
+  int32_t  camera_embedding_dim, num_cameras;
+  int32_t  color_in_width;           /* 32 (no embedding) or 48: width of the padded colour-net input */
 } hrf_field;
 
 /* Sample source: either explicit per-sample queries (QueryInput, query_io.py:6-13) or the
@@ -132,6 +137,11 @@ typedef struct {
   const float* sample_distances;     /* [N] */
   const int64_t* ray_indices;        /* [N] sorted ascending */
   int64_t num_samples;
+  /* camera numbers, only read when the field has camera embeddings and use_camera_embeddings != 0
+   * (is_training; at evaluation the embedding is all zeros, humanrf.py:196-204) */
+  const int32_t* camera_numbers;     /* query form: [N] */
+  const int32_t* ray_camera_numbers; /* ray-batch form: [R] */
+  int32_t use_camera_embeddings;
 } hrf_samples;
 
 /* mode: 0 = density only (sigma, geo), 1 = density + radiance.  Any output may be NULL.
@@ -191,8 +201,9 @@ typedef struct {
 int hrf_field_backward(const hrf_field* f, const hrf_samples* s, const hrf_segment_grads* seg_grads /* device array */,
                        const float* d_sigma /* [N] */, const float* d_rgb /* [N,3] or NULL */,
                        const void* feat_bf16 /* [N,32] from hrf_field_forward, or NULL to re-encode */,
-                       float* d_mlp /* fp32 [10240]: sigma W1,W2, colour W1,W2,W3 row-major [out,in] */,
-                       void* workspace /* 128 bytes per sample: d(composed features), level-major */, void* stream);
+                       float* d_mlp /* fp32 [3072 + 64*color_in_width + 5120]: sigma W1,W2, colour W1,W2,W3 row-major [out,in] */,
+                       float* d_camera_embeddings /* fp32 [num_cameras, dim] accumulated into, or NULL */,
+                       void* workspace /* 160 bytes per sample (16-byte aligned): d(features) level-major, positions, segment ids */, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * tensor_composition_native parity (tensor_composition.cu:120-219): stand-alone fwd/bwd of

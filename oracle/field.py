@@ -134,12 +134,14 @@ class OracleModel:
     w_color: List[torch.Tensor]        # [64,32], [64,64], [16,64]
     density_scale: float = 100.0
     bf16: bool = False
+    camera_embeddings: torch.Tensor = None   # [160, E] or None (humanrf.py:75-76)
 
     def parameters(self):
         ps = []
         for s in self.segments:
             ps += list(s.grids) + [s.vectors]
-        return ps + list(self.w_sigma) + list(self.w_color)
+        ps = ps + list(self.w_sigma) + list(self.w_color)
+        return ps + ([self.camera_embeddings] if self.camera_embeddings is not None else [])
 
     def _q(self, x):
         return rbf(x) if self.bf16 else x
@@ -172,10 +174,21 @@ class OracleModel:
         o = h @ w2.t()
         return truncated_exp(o[:, 0]) * self.density_scale, o[:, 1:]
 
-    def color_head(self, directions, geo):
-        """humanrf.py:188-206 : [SH16 | geo15 | pad 1.0] -> 64 ReLU -> 64 ReLU -> 16 -> sigmoid[:3]."""
+    def color_head(self, directions, geo, camera_numbers=None):
+        """humanrf.py:188-206 : [SH16 | geo15 | camera embedding E (zeros at evaluation) | pad 1.0 to 32/48]
+        -> 64 ReLU -> 64 ReLU -> 16 -> sigmoid[:3]."""
         n = directions.shape[0]
-        inp = torch.cat((self._q(sh4(directions)), self._q(geo), torch.ones((n, 1), dtype=geo.dtype)), dim=1)
+        parts = [self._q(sh4(directions)), self._q(geo)]
+        if self.camera_embeddings is not None:
+            E = self.camera_embeddings.shape[1]
+            if camera_numbers is not None:
+                parts.append(self._q(self.camera_embeddings[camera_numbers.reshape(-1).long()]))
+            else:
+                parts.append(torch.zeros((n, E), dtype=geo.dtype))
+        width = self.w_color[0].shape[1]
+        have = sum(p.shape[1] for p in parts)
+        parts.append(torch.ones((n, width - have), dtype=geo.dtype))
+        inp = torch.cat(parts, dim=1)
         w1, w2, w3 = [self._q(w) for w in self.w_color]
         h = self._q(torch.relu(inp @ w1.t()))
         h = self._q(torch.relu(h @ w2.t()))
@@ -184,13 +197,14 @@ class OracleModel:
     def density(self, positions, frame_numbers):
         return self.sigma_head(self.features(positions, frame_numbers))
 
-    def forward(self, positions, directions, frame_numbers):
+    def forward(self, positions, directions, frame_numbers, camera_numbers=None):
         sigma, geo = self.density(positions, frame_numbers)
-        return sigma, geo, self.color_head(directions, geo)
+        return sigma, geo, self.color_head(directions, geo, camera_numbers)
 
 
 def make_model(segment_sizes=(50,), sorted_frame_numbers=None, seed=123, table_init="trained",
-               bf16=False, dtype=torch.float32, requires_grad=False, table_std=0.05) -> OracleModel:
+               bf16=False, dtype=torch.float32, requires_grad=False, table_std=0.05,
+               camera_embedding_dim=0) -> OracleModel:
     """Synthetic parameters per SURVEY 8(d): tables U(-1e-4,1e-4) ("tcnn") or N(0,table_std)
     ("trained"), vectors N(0,0.1) (decomposition4d.py:76-78), Xavier-uniform MLP weights."""
     g = torch.Generator().manual_seed(seed)
@@ -215,8 +229,11 @@ def make_model(segment_sizes=(50,), sorted_frame_numbers=None, seed=123, table_i
         a = float(np.sqrt(6.0 / (i + o)))
         return ((torch.rand((o, i), generator=g) * 2 - 1) * a).to(dtype)
 
+    k = 32 if camera_embedding_dim == 0 else 48
     m = OracleModel(segs, f2s, f2t, [xavier(64, 32), xavier(16, 64)],
-                    [xavier(64, 32), xavier(64, 64), xavier(16, 64)], 100.0, bf16)
+                    [xavier(64, k), xavier(64, 64), xavier(16, 64)], 100.0, bf16)
+    if camera_embedding_dim > 0:
+        m.camera_embeddings = torch.randn((160, camera_embedding_dim), generator=g).to(dtype)   # nn.Embedding init N(0,1)
     if requires_grad:
         for p in m.parameters():
             p.requires_grad_(True)

@@ -133,3 +133,34 @@ def test_adam_step_matches_torch(cuda):
                                       1e-2, 0.9, 0.99, 1e-15, step, 1.0, L.stream()))
         np.testing.assert_allclose(p.cpu().numpy(), p_ref.detach().cpu().numpy(), rtol=2e-6, atol=2e-7)
     torch.testing.assert_close(shadow.float(), p.to(torch.bfloat16).float(), rtol=0, atol=0)
+
+
+def test_camera_embedding_gradients(cuda):
+    """render() in training mode with camera_embedding_dim=2: gradients of every parameter incl. the embedding table."""
+    from humanrf_b200.volume_rendering import render
+
+    om, m, frames = make_pair((6,), table_std=4.0, cam_emb=2)
+    for p in om.parameters():
+        p.requires_grad_(True)
+    b = synthetic_rays(120, 40, frames, ragged=True, seed=8)
+    ib = input_batch_of(b, cuda)
+    nr = ib.num_rays
+    g = torch.Generator().manual_seed(2)
+    bg = torch.rand(nr, 3, generator=g)
+    out = render(ib, m, bg.to(cuda), is_training=True)
+    loss, _ = R.training_loss(out.color, out.weights_sum, ib.rgba, bg.to(cuda))
+    loss.backward()
+    pos = positions_of(b)
+    s_o, _, c_o = om.forward(pos, b["d"][b["ri"]], b["frames"][b["ri"]], b["cams"][b["ri"]])
+    col_o, ws_o = R.render(b["t"], s_o, c_o, b["ri"], nr, bg)
+    loss_o, _ = R.training_loss(col_o, ws_o, b["rgba"], bg)
+    loss_o.backward()
+    assert abs(loss.item() - loss_o.item()) < 2e-3 * max(1.0, abs(loss_o.item()))
+    refs = [om.segments[0].grids[k].grad.reshape(-1) for k in range(4)] + [om.segments[0].vectors.grad]
+    refs += [torch.cat([w.grad.reshape(-1) for w in om.w_sigma]), torch.cat([w.grad.reshape(-1) for w in om.w_color]),
+             om.camera_embeddings.grad]
+    for p, ref in zip(m.hot_parameters(), refs):
+        e = _relnorm(p.grad.cpu(), ref)
+        print("param", tuple(p.shape), "relnorm", f"{e:.3e}")
+        assert e < 5e-2
+    assert (m.camera_embeddings.weight.grad != 0).any()

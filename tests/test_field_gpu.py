@@ -97,3 +97,22 @@ def test_fp32_oracle_tolerance(cuda):
     err = np.abs(rgb.cpu().numpy() - orgb.numpy())
     print("vs fp32 oracle: density rel max", rel.max(), "radiance abs max", err.max())
     assert rel.max() < 1e-1 and np.median(rel) < 1e-2 and err.max() < 2e-2
+
+
+@pytest.mark.parametrize("training", [True, False])
+def test_camera_embeddings(cuda, training):
+    """camera_embedding_dim=2 (example_humanrf.py:19): colour input widens to 48 with the embedding at features 31,32;
+    looked up while training, zeros at evaluation (humanrf.py:194-204)."""
+    om, m, frames = make_pair((6,), cam_emb=2)
+    b = synthetic_rays(96, 24, frames, ragged=True)
+    pos, dirs, fr, cams = positions_of(b), b["d"][b["ri"]], b["frames"][b["ri"]], b["cams"][b["ri"]]
+    with torch.no_grad():
+        osig, _, orgb = om.forward(pos, dirs, fr, cams if training else None)
+        _, _, orgb_other = om.forward(pos, dirs, fr, None if training else cams)
+    q = QueryInput(is_training=training, positions=pos.to(cuda), directions=dirs.to(cuda), frame_numbers=fr.view(-1, 1).to(cuda),
+                   camera_numbers=cams.view(-1, 1).to(cuda))
+    with torch.no_grad():
+        out = m(q)
+    _check(out.density.cpu().numpy(), out.radiance.cpu().numpy(), osig.numpy(), orgb.numpy(), f"cam-emb training={training}")
+    assert np.abs(orgb.numpy() - orgb_other.numpy()).max() > 2e-2, "the embedding must matter for this check to mean anything"
+    assert len(m.get_params(1e-2)) == 4 and "camera_embeddings.weight" in m.state_dict()

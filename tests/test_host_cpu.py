@@ -84,11 +84,16 @@ def test_grid_layout_matches_oracle_and_survey():
     assert [ofield.segment_log2_hashmap_size(s) for s in (6, 12, 25, 50, 100)] == [15, 16, 17, 18, 19]
 
 
-def test_mlp_blob_permutation_is_a_bijection():
-    perm = mlp_blob_permutation()
-    assert sorted(perm.tolist()) == list(range(10240))
+def test_mlp_blob_permutation():
+    for emb, n in ((0, 10240), (2, 11264)):
+        dst, src = mlp_blob_permutation(emb)
+        assert sorted(src.tolist()) == list(range(n)) and len(set(dst.tolist())) == n and dst.max() < 22528 // 2
+    dst, src = mlp_blob_permutation(0)
     # element (n=9, k=17) of the first layer [64,32]: core (kg=2, ng=1), row 1, col 1
-    assert perm[(2 * 8 + 1) * 64 + 1 * 8 + 1] == 9 * 32 + 17
+    assert src[dst.tolist().index((2 * 8 + 1) * 64 + 1 * 8 + 1)] == 9 * 32 + 17
+    # colour W2 starts at byte 12288 whatever the colour input width
+    dst48, src48 = mlp_blob_permutation(2)
+    assert dst48[src48.tolist().index(3072 + 64 * 48)] == 12288 // 2
 
 
 def test_c_abi_exports_every_declared_symbol():
