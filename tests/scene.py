@@ -56,3 +56,61 @@ def make_scene(num_images=4, width=96, height=72, G=128, seed=0, portrait_every=
         camera_numbers=rng.integers(0, 160, num_images).astype(np.int32),
         rgba=rng.integers(0, 256, (P, 4)).astype(np.uint8), light_mask=rng.random(P) < 0.05,
         aabb=np.array([[-0.45, -0.5, -0.4], [0.5, 0.45, 0.5]], np.float32))
+
+
+class _Cam:
+    def __init__(self, width, height, rot, translation, f=1.773863):
+        self.width, self.height = width, height
+        self.rotation_axisangle, self.translation = np.asarray(rot, float), np.asarray(translation, float)
+        self.focal_length, self.principal_point = np.array([f, f * width / height]), np.array([0.5, 0.5])
+
+    def projection_matrix_world2pixel(self):
+        return projection_matrix_world2pixel(self.width, self.height, self.rotation_axisangle, self.translation,
+                                             self.focal_length, self.principal_point)
+
+
+class SyntheticDataset:
+    """Duck-typed stand-in for actorshq.dataset.volumetric_dataset.VolumetricDataset (the methods DataLoader calls)."""
+
+    def __init__(self, num_cameras=5, frames=range(15, 21), width=64, height=48, G=64, seed=0):
+        import copy
+
+        self._copy = copy
+        rng = np.random.default_rng(seed)
+        self.frames = list(frames)
+        self.cameras = []
+        for i in range(num_cameras):
+            a = 2 * np.pi * i / num_cameras + 0.2
+            pos = np.array([3.0 * np.cos(a), rng.uniform(-0.5, 0.5), 3.0 * np.sin(a)]) + np.array([0.3, 1.0, -0.2])
+            w2p = look_at_camera(pos - np.array([0.3, 1.0, -0.2]), width, height)   # reuse the rotation of a centred camera
+            fwd = -(pos - np.array([0.3, 1.0, -0.2])); fwd /= np.linalg.norm(fwd)
+            up = np.array([0.0, -1.0, 0.0]); right = np.cross(fwd, up); right /= np.linalg.norm(right); down = np.cross(fwd, right)
+            Rm = np.stack([right, down, fwd], 1)
+            ang = np.arccos(np.clip((np.trace(Rm) - 1) / 2, -1, 1))
+            aa = ang / (2 * np.sin(ang)) * np.array([Rm[2, 1] - Rm[1, 2], Rm[0, 2] - Rm[2, 0], Rm[1, 0] - Rm[0, 1]])
+            self.cameras.append(_Cam(width, height, aa, pos))
+        self.aabb = np.array([[-0.45, 0.25, -0.95], [1.05, 1.75, 0.55]])       # world-space box (extent 1.5) around (0.3,1,-0.2)
+        self._grids = {f: ellipsoid_grid(G, seed + k % 2) for k, f in enumerate(self.frames)}
+        self._rng_seed = seed
+
+    def get_aabb(self, frame_numbers=None):
+        return self.aabb
+
+    def get_scaled_cameras(self, scene_offset, scene_scale):
+        cams = self._copy.deepcopy(self.cameras)
+        for c in cams:
+            c.translation = (c.translation + scene_offset) * scene_scale
+        return cams
+
+    def get_rgb(self, camera_number, frame_number, normalize=True):
+        rng = np.random.default_rng(self._rng_seed * 7919 + camera_number * 131 + frame_number)
+        c = self.cameras[camera_number]
+        return rng.integers(0, 256, (c.height, c.width, 3)).astype(np.float32) / np.float32(255)
+
+    def get_mask(self, camera_number, frame_number, normalize=True):
+        rng = np.random.default_rng(self._rng_seed * 104729 + camera_number * 17 + frame_number)
+        c = self.cameras[camera_number]
+        return (rng.random((c.height, c.width, 1)) > 0.4).astype(np.float32)
+
+    def get_occupancy_grid(self, frame_number):
+        return self._grids[frame_number]
