@@ -337,7 +337,10 @@ def main():
             "gpu_launches": gpu_launches,
             "clocks": clk,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": which, "kernel": "field_forward_kernel" if args.mode == "render" else "train step",
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one field_forward_kernel launch on this very batch,
+                         # from the committed ncu --set full capture (profiles/r1_ncu_full_fwd_raw.csv)
+                         "traffic": 118.8e6 if args.mode == "render" else None, "traffic_unit": "bytes/launch",
+                         "peak_source": which, "kernel": "field_forward_kernel" if args.mode == "render" else "train step",
                          "kernel_ms": kern_ms, "algorithmic_bytes_per_sample": ALG_BYTES_FWD if args.mode == "render" else 12300},
             "wall_s_timed_loop": t_wall,
         }
