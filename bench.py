@@ -232,7 +232,7 @@ def main():
 
     def step_render(ev=None):
         L.check(lib.hrf_field_forward(C.byref(nat.field), C.byref(samples), 1, 0, sigma.data_ptr(), None, rgb.data_ptr(),
-                                      None, L.stream()))
+                                      None, None, L.stream()))
         if ev is not None:
             ev.record()
         off = ray_offsets(g["ri"], RAYS)

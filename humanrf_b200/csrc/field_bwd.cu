@@ -17,7 +17,7 @@
 namespace hrf {
 
 struct __align__(1024) BwdSmem {
-  unsigned char w[kWBlobBytes];
+  unsigned char w[kWBlobBytesMax];
   unsigned char feat[kTile * 32 * 2];  // composed features            (A32)
   unsigned char cin[kTile * 48 * 2];   // colour-net input              (A32 / A48)
   unsigned char hs[kTile * 64 * 2];    // sigma hidden, then d(hidden)  (A64)
@@ -146,6 +146,7 @@ struct ScatterArgs {
   const float2* dfeat;  // [16 levels][N] float2, written by field_backward_kernel
   const float4* pos4;   // [N] (x,y,z,t), written by field_backward_kernel
   const uint8_t* seg8;  // [N]
+  const uint32_t* egrid;  // bf16x2 [16*4][N] per-grid features saved by the forward, or NULL (re-gather the tables)
 };
 
 __global__ void __launch_bounds__(256, 3) grid_scatter_kernel(const __grid_constant__ ScatterArgs a) {
@@ -210,9 +211,11 @@ __global__ void __launch_bounds__(256, 3) grid_scatter_kernel(const __grid_const
       const hrf_segment* sg = s.seg;
       const uint32_t off = sg->level_offset[l];
       corner_indices((sg->hashed_mask >> l) & 1u, res, sg->level_size[l], A, B, C, idx);
-      const uint32_t* tab = sg->grid[k] + off;
+      if (a.egrid == nullptr) {
+        const uint32_t* tab = sg->grid[k] + off;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) raw[q] = __ldg(tab + idx[q]);
+        for (int q = 0; q < 8; ++q) raw[q] = __ldg(tab + idx[q]);
+      }
       if (sg != cur_seg) {
         flush_tap();
         to0 = 0xffffffffu;
@@ -231,8 +234,16 @@ __global__ void __launch_bounds__(256, 3) grid_scatter_kernel(const __grid_const
     for (int q = 0; q < 8; ++q) {
       accx[q] = __fmaf_rn(w[q], gx, accx[q]);
       accy[q] = __fmaf_rn(w[q], gy, accy[q]);
-      ex = __fmaf_rn(w[q], bf16_lo(raw[q]), ex);
-      ey = __fmaf_rn(w[q], bf16_hi(raw[q]), ey);
+    }
+    if (a.egrid != nullptr) {  // interpolated grid features saved by the forward
+      const uint32_t ev = __ldg(a.egrid + (size_t)blockIdx.y * n + i);
+      ex = bf16_lo(ev), ey = bf16_hi(ev);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        ex = __fmaf_rn(w[q], bf16_lo(raw[q]), ex);
+        ey = __fmaf_rn(w[q], bf16_hi(raw[q]), ey);
+      }
     }
     // d vectors[axis][i0/i1][2l..2l+1] = e_k * dOut * (1-frac | frac)   (tensor_composition.cu:109-111)
     if (tp.o0 != to0 || tp.o1 != to1) {
@@ -267,8 +278,8 @@ __global__ void __launch_bounds__(kTile, 2) field_backward_kernel(const __grid_c
   __syncthreads();
   tc_fence_after();
   if (tid == 0) {
-    mbar_arrive_expect_tx(&sm.bar_w, kWBlobBytes);
-    tma_load_1d(sm.w, f.mlp_blob, kWBlobBytes, &sm.bar_w);
+    mbar_arrive_expect_tx(&sm.bar_w, w_blob_bytes(f.color_in_width));
+    tma_load_1d(sm.w, f.mlp_blob, w_blob_bytes(f.color_in_width), &sm.bar_w);
   }
   const uint32_t tm = sm.tmem_base;
   const uint32_t trow = tm + ((uint32_t)(tid & ~31) << 16);  // this warp's TMEM lanes
@@ -283,7 +294,7 @@ __global__ void __launch_bounds__(kTile, 2) field_backward_kernel(const __grid_c
   for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     const int64_t i = tile * kTile + tid;
     const bool valid = i < n;
-    const Sample s = load_sample(f, args.s, i, true);
+    const Sample s = load_sample(f, args.s, i);
     if (valid) {
       args.pos4[i] = make_float4(s.x, s.y, s.z, s.t);
       args.seg8[i] = s.seg != nullptr ? (uint8_t)(s.seg - f.segments) : (uint8_t)255;
@@ -308,15 +319,16 @@ __global__ void __launch_bounds__(kTile, 2) field_backward_kernel(const __grid_c
     mma_round(sm, phase, [&] { issue_layer(tm + kColWork, a_hs, wbase + kWSig2, 16, 64); });
     tmem_ld16(trow + kColWork, o);
     const float h0 = o[0];
-    write_color_input(f, sm.cin, roff, s, o);
+    const View vw = load_view(f, args.s, i);
+    write_color_input(f, sm.cin, roff, vw, o);
     const int K1 = f.color_in_width;
     mma_round(sm, phase, [&] { issue_layer(tm + kColWork, a_cin, wbase + kWCol1, 64, K1); });
     tmem_ld64(trow + kColWork, v);
     store_relu64(sm.h1, roff, v);
-    mma_round(sm, phase, [&] { issue_layer(tm + kColWork, a_h1, wbase + kWCol2, 64, 64); });
+    mma_round(sm, phase, [&] { issue_layer(tm + kColWork, a_h1, wbase + w_col2(f.color_in_width), 64, 64); });
     tmem_ld64(trow + kColWork, v);
     store_relu64(sm.h2, roff, v);
-    mma_round(sm, phase, [&] { issue_layer(tm + kColWork, a_h2, wbase + kWCol3, 16, 64); });
+    mma_round(sm, phase, [&] { issue_layer(tm + kColWork, a_h2, wbase + w_col3(f.color_in_width), 16, 64); });
     tmem_ld16(trow + kColWork, o);
 
     // ---------------- backward ----------------
@@ -335,13 +347,13 @@ __global__ void __launch_bounds__(kTile, 2) field_backward_kernel(const __grid_c
     }
     mma_round(sm, phase, [&] {
       issue_wgrad(tm + kColW3c, a_h2, a_g3, 16, have_acc);                   // dW3c^T += H2^T dO3
-      issue_dgrad(tm + kColWork, a_g3, wbase + kWCol3, 64, 16);              // dH2 = dO3 W3c
+      issue_dgrad(tm + kColWork, a_g3, wbase + w_col3(f.color_in_width), 64, 16);              // dH2 = dO3 W3c
     });
     tmem_ld64(trow + kColWork, v);
     relu_backward_inplace64(sm.h2, roff, v);
     mma_round(sm, phase, [&] {
       issue_wgrad(tm + kColW2c, a_h2, a_h1, 64, have_acc);                   // dW2c += dH2^T H1
-      issue_dgrad(tm + kColWork, a_h2, wbase + kWCol2, 64, 64);              // dH1 = dH2 W2c
+      issue_dgrad(tm + kColWork, a_h2, wbase + w_col2(f.color_in_width), 64, 64);              // dH1 = dH2 W2c
     });
     tmem_ld64(trow + kColWork, v);
     relu_backward_inplace64(sm.h1, roff, v);
@@ -353,11 +365,11 @@ __global__ void __launch_bounds__(kTile, 2) field_backward_kernel(const __grid_c
       float dc[48];
       tmem_ld32(trow + kColWork, dc);
       if (K1 == 48) tmem_ld16(trow + kColWork + 32, dc + 32);
-      if (args.d_emb != nullptr && s.cam >= 0) {  // d(camera embedding): colour-input features 31..30+E
+      if (args.d_emb != nullptr && vw.cam >= 0) {  // d(camera embedding): colour-input features 31..30+E
         const int E = f.camera_embedding_dim;
 #pragma unroll
         for (int e = 0; e < HRF_MAX_CAMERA_EMBEDDING_DIM; ++e)
-          if (e < E) atomicAdd(args.d_emb + (size_t)s.cam * E + e, dc[31 + e]);
+          if (e < E) atomicAdd(args.d_emb + (size_t)vw.cam * E + e, dc[31 + e]);
       }
       // d(sigma-net output): col 0 from the density (truncated_exp backward, activation.py:21), 1..15 = d geo
       float dh0 = 0.f;
@@ -430,8 +442,9 @@ __global__ void __launch_bounds__(kTile, 2) field_backward_kernel(const __grid_c
 using namespace hrf;
 
 extern "C" int hrf_field_backward(const hrf_field* f, const hrf_samples* s, const hrf_segment_grads* seg_grads,
-                                  const float* d_sigma, const float* d_rgb, const void* feat_bf16, float* d_mlp,
-                                  float* d_camera_embeddings, void* workspace, void* stream) {
+                                  const float* d_sigma, const float* d_rgb, const void* feat_bf16,
+                                  const void* grid_feat_bf16, float* d_mlp, float* d_camera_embeddings, void* workspace,
+                                  void* stream) {
   HRF_REQUIRE(f != nullptr && s != nullptr && seg_grads != nullptr, "null argument");
   HRF_REQUIRE(f->num_segments < 255, "at most 254 temporal segments");
   if (s->num_samples == 0) return 0;
@@ -469,6 +482,7 @@ extern "C" int hrf_field_backward(const hrf_field* f, const hrf_samples* s, cons
   sa.dfeat = a.dfeat;
   sa.pos4 = a.pos4;
   sa.seg8 = a.seg8;
+  sa.egrid = reinterpret_cast<const uint32_t*>(grid_feat_bf16);
   {
     const int64_t chunks = (s->num_samples + kChunk - 1) / kChunk;
     grid_scatter_kernel<<<dim3((unsigned)((chunks + 255) / 256), HRF_N_LEVELS * 4), 256, 0, st>>>(sa);

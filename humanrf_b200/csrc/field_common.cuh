@@ -14,10 +14,11 @@ constexpr uint32_t kPrimeZ = 805459861u;
 // element (n,k) of W[N,K] at ((k/8)*(N/8) + n/8)*128 + (n%8)*16 + (k%8)*2).
 constexpr uint32_t kWSig1 = 0;       // sigma  W1 [64,32]
 constexpr uint32_t kWSig2 = 4096;    // sigma  W2 [16,64]
-constexpr uint32_t kWCol1 = 6144;    // colour W1 [64,32] or [64,48] (room for 48: the k-chunk stride does not depend on K)
-constexpr uint32_t kWCol2 = 12288;   // colour W2 [64,64]
-constexpr uint32_t kWCol3 = 20480;   // colour W3 [16,64]
-constexpr uint32_t kWBlobBytes = HRF_MLP_BLOB_BYTES;
+constexpr uint32_t kWCol1 = 6144;    // colour W1 [64,K], K = 32 | 48
+__host__ __device__ constexpr uint32_t w_col2(int K) { return kWCol1 + 128u * (uint32_t)K; }   // colour W2 [64,64]
+__host__ __device__ constexpr uint32_t w_col3(int K) { return w_col2(K) + 8192u; }             // colour W3 [16,64]
+__host__ __device__ constexpr uint32_t w_blob_bytes(int K) { return w_col3(K) + 2048u; }       // 20480 | 22528
+constexpr uint32_t kWBlobBytesMax = HRF_MLP_BLOB_BYTES;
 // row-major fp32 gradient buffer offsets (elements)
 constexpr int kGSig1 = 0, kGSig2 = 2048, kGCol1 = 3072;  // colour W2 at 3072 + 64*K, colour W3 4096 later (K = 32 | 48)
 
@@ -48,24 +49,26 @@ struct FieldArgs {
   uint32_t* geo;   // bf16 [N,16] viewed as u32 pairs
   float* rgb;
   uint4* feat;     // bf16 [N,32] composed features (optional output)
+  uint32_t* egrid; // bf16x2 [16*4][N] per-grid interpolated features (optional output, for the backward scatter)
   int mode;
 };
 
 struct Sample {
   float x, y, z, t;        // normalised coordinates in [0,1] (positions + 0.5, local time)
-  float dx, dy, dz;        // view direction
   const hrf_segment* seg;  // segment descriptor (NULL for padding threads)
+};
+// View direction and camera row of a sample.  Loaded separately, AFTER the gather phase, so that these four values do
+// not occupy registers during the 512-gather loop (the re-read hits L1/L2).
+struct View {
+  float dx, dy, dz;
   int cam;                 // camera row of the embedding table, or -1 (zeros: evaluation / no embedding)
 };
 
-__device__ __forceinline__ Sample load_sample(const hrf_field& f, const hrf_samples& s, int64_t i, bool need_dir) {
+__device__ __forceinline__ Sample load_sample(const hrf_field& f, const hrf_samples& s, int64_t i) {
   Sample o;
   o.seg = nullptr;
   o.x = o.y = o.z = o.t = 0.f;
-  o.dx = o.dy = o.dz = 0.f;
-  o.cam = -1;
   if (i >= s.num_samples) return o;
-  const bool want_cam = need_dir && s.use_camera_embeddings && f.camera_embeddings != nullptr;
   int frame;
   float px, py, pz;
   if (s.ray_origins != nullptr) {
@@ -74,21 +77,14 @@ __device__ __forceinline__ Sample load_sample(const hrf_field& f, const hrf_samp
     const float t = __ldg(s.sample_distances + i);
     const float* ro = s.ray_origins + 3 * r;
     const float* rd = s.ray_directions + 3 * r;
-    o.dx = __ldg(rd), o.dy = __ldg(rd + 1), o.dz = __ldg(rd + 2);
-    px = __fadd_rn(__ldg(ro), __fmul_rn(t, o.dx));
-    py = __fadd_rn(__ldg(ro + 1), __fmul_rn(t, o.dy));
-    pz = __fadd_rn(__ldg(ro + 2), __fmul_rn(t, o.dz));
+    px = __fadd_rn(__ldg(ro), __fmul_rn(t, __ldg(rd)));
+    py = __fadd_rn(__ldg(ro + 1), __fmul_rn(t, __ldg(rd + 1)));
+    pz = __fadd_rn(__ldg(ro + 2), __fmul_rn(t, __ldg(rd + 2)));
     frame = __ldg(s.ray_frame_numbers + r);
-    if (want_cam && s.ray_camera_numbers != nullptr) o.cam = __ldg(s.ray_camera_numbers + r);
   } else {
     px = __ldg(s.positions + 3 * i), py = __ldg(s.positions + 3 * i + 1), pz = __ldg(s.positions + 3 * i + 2);
-    if (need_dir && s.directions != nullptr) {
-      o.dx = __ldg(s.directions + 3 * i), o.dy = __ldg(s.directions + 3 * i + 1), o.dz = __ldg(s.directions + 3 * i + 2);
-    }
     frame = __ldg(s.frame_numbers + i);
-    if (want_cam && s.camera_numbers != nullptr) o.cam = __ldg(s.camera_numbers + i);
   }
-  if (o.cam < 0 || o.cam >= f.num_cameras) o.cam = -1;
   // humanrf.py:175 : positions + 0.5 ; :176 normalised local frame number
   o.x = __fadd_rn(px, 0.5f), o.y = __fadd_rn(py, 0.5f), o.z = __fadd_rn(pz, 0.5f);
   int sg = -1;
@@ -98,6 +94,26 @@ __device__ __forceinline__ Sample load_sample(const hrf_field& f, const hrf_samp
   }
   if (sg >= 0 && sg < f.num_segments) o.seg = f.segments + sg;
   return o;
+}
+
+__device__ __forceinline__ View load_view(const hrf_field& f, const hrf_samples& s, int64_t i) {
+  View v;
+  v.dx = v.dy = v.dz = 0.f;
+  v.cam = -1;
+  if (i >= s.num_samples) return v;
+  const bool want_cam = s.use_camera_embeddings && f.camera_embeddings != nullptr;
+  if (s.ray_origins != nullptr) {
+    const int64_t r = __ldg(s.ray_indices + i);
+    const float* rd = s.ray_directions + 3 * r;
+    v.dx = __ldg(rd), v.dy = __ldg(rd + 1), v.dz = __ldg(rd + 2);
+    if (want_cam && s.ray_camera_numbers != nullptr) v.cam = __ldg(s.ray_camera_numbers + r);
+  } else {
+    if (s.directions != nullptr)
+      v.dx = __ldg(s.directions + 3 * i), v.dy = __ldg(s.directions + 3 * i + 1), v.dz = __ldg(s.directions + 3 * i + 2);
+    if (want_cam && s.camera_numbers != nullptr) v.cam = __ldg(s.camera_numbers + i);
+  }
+  if (v.cam < 0 || v.cam >= f.num_cameras) v.cam = -1;
+  return v;
 }
 
 struct Cell {
@@ -213,7 +229,7 @@ __device__ __forceinline__ void sh4(float dx, float dy, float dz, float* o) {
 
 // Colour-net input row (humanrf.py:192-206 + tcnn Composite[SH(4) on 3 dims, Identity] padded with 1.0):
 // [SH 0..15 | geo 16..30 | camera embedding 31..30+E | 1.0 ...] as bf16, K = 32 (E = 0) or 48.
-__device__ __forceinline__ void write_color_input(const hrf_field& f, unsigned char* abuf, uint32_t roff, const Sample& s,
+__device__ __forceinline__ void write_color_input(const hrf_field& f, unsigned char* abuf, uint32_t roff, const View& s,
                                                   const float* o /* sigma-net output, o[1..15] = geo */) {
   float sh[16];
   sh4(s.dx, s.dy, s.dz, sh);
@@ -243,7 +259,12 @@ __device__ __forceinline__ void write_color_input(const hrf_field& f, unsigned c
 
 // Encode one sample (4 grids x 16 levels, composed with the vector lerps) and write the 32
 // bf16 features of row `row` into the K-major A tile at `abuf` (shared memory).
-__device__ __forceinline__ void encode_to_smem(const hrf_field& f, const Sample& s, unsigned char* abuf, int row) {
+// If `egrid` is not NULL the per-grid interpolated features e_k (before composition) are also stored, bf16x2, as
+// egrid[(level*4 + grid) * n + i]: the backward scatter needs them for the vector gradients and then does not have
+// to gather the tables a second time.
+template <bool kSaveGrid = false>
+__device__ __forceinline__ void encode_to_smem(const hrf_field& f, const Sample& s, unsigned char* abuf, int row,
+                                               uint32_t* egrid = nullptr, int64_t i = 0, int64_t n = 0) {
   const uint32_t roff = a_row_off(row);
   if (s.seg == nullptr) {
 #pragma unroll
@@ -283,6 +304,13 @@ __device__ __forceinline__ void encode_to_smem(const hrf_field& f, const Sample&
       const float o0 = e0.x * vt.x + e1.x * vz.x + e2.x * vx.x + e3.x * vy.x;
       const float o1 = e0.y * vt.y + e1.y * vz.y + e2.y * vx.y + e3.y * vy.y;
       pk[j] = pack_bf16x2(o0, o1);
+      if (kSaveGrid && egrid != nullptr) {
+        uint32_t* eg = egrid + (size_t)(4 * l) * n + i;
+        eg[0] = pack_bf16x2(e0.x, e0.y);
+        eg[n] = pack_bf16x2(e1.x, e1.y);
+        eg[2 * n] = pack_bf16x2(e2.x, e2.y);
+        eg[3 * n] = pack_bf16x2(e3.x, e3.y);
+      }
     }
     *reinterpret_cast<uint4*>(abuf + kg * kAChunk + roff) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
   }

@@ -6,6 +6,7 @@
 // encode -> MLP chain stays in registers / shared memory / TMEM.
 // Reference semantics: humanrf/scene_representation/humanrf.py:158-208,
 // decomposition4d.py:124-135, native/tensor_composition.cu:9-55.
+#include <stddef.h>
 #include <stdlib.h>
 
 #include "field_common.cuh"
@@ -15,8 +16,10 @@ namespace hrf {
 
 // One activation buffer serves every layer: a layer's output tile is written over its input tile, which is safe
 // because each thread writes only after the tcgen05.commit barrier of the MMA that read the old tile.
+// The weight blob comes LAST and only its used part is requested as dynamic shared memory (20 KB without camera
+// embeddings): 5 CTAs/SM then need 190 KB, which keeps the SM in the 196 KB shared-memory carve-out and leaves 60 KB
+// of L1 for the gathers (2 KB more per CTA tips it into the 228 KB carve-out and costs 20 % of the kernel time).
 struct __align__(128) FwdSmem {
-  unsigned char w[kWBlobBytes];       // packed weights (TMA bulk copy, once per CTA)
   unsigned char a[kTile * 64 * 2];    // A tile: K = 32 layout in the first 8 KB, or K = 64 layout (hidden activations)
   uint64_t bar_w;                     // weights landed
   uint64_t bar_mma;                   // tcgen05.commit arrival
@@ -24,6 +27,7 @@ struct __align__(128) FwdSmem {
   // early-stop schedule: the current work item, published by thread 0
   int64_t item_start, item_end;
   int32_t item_ray, item_skip;
+  __align__(128) unsigned char w[kWBlobBytesMax];   // packed weights (TMA bulk copy, once per CTA)
 };
 
 __device__ __forceinline__ float warp_sum_fwd(float v) {
@@ -97,7 +101,7 @@ __device__ __forceinline__ void store_hidden(unsigned char* hbuf, int row, const
   }
 }
 
-template <bool kSimt, int kCtasPerSm>
+template <bool kSimt, int kCtasPerSm, bool kSaveGrid = false>
 __global__ void __launch_bounds__(kTile, kCtasPerSm) field_forward_kernel(const __grid_constant__ FieldArgs args) {
   extern __shared__ unsigned char smem_raw[];
   FwdSmem& sm = *reinterpret_cast<FwdSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
@@ -120,8 +124,8 @@ __global__ void __launch_bounds__(kTile, kCtasPerSm) field_forward_kernel(const 
   __syncthreads();
   if constexpr (!kSimt) tc_fence_after();
   if (tid == 0) {
-    mbar_arrive_expect_tx(&sm.bar_w, kWBlobBytes);
-    tma_load_1d(sm.w, f.mlp_blob, kWBlobBytes, &sm.bar_w);
+    mbar_arrive_expect_tx(&sm.bar_w, w_blob_bytes(f.color_in_width));
+    tma_load_1d(sm.w, f.mlp_blob, w_blob_bytes(f.color_in_width), &sm.bar_w);
   }
   bool weights_ready = false;
   uint32_t phase = 0;
@@ -177,8 +181,8 @@ __global__ void __launch_bounds__(kTile, kCtasPerSm) field_forward_kernel(const 
         continue;
       }
     }
-    const Sample s = load_sample(f, args.s, valid ? i : n, args.mode != 0);
-    encode_to_smem(f, s, sm.a, tid);
+    const Sample s = load_sample(f, args.s, valid ? i : n);
+    encode_to_smem<kSaveGrid>(f, s, sm.a, tid, (kSaveGrid && valid && s.seg != nullptr) ? args.egrid : nullptr, i, n);
     if (args.feat != nullptr && valid) {
       const uint32_t ro = a_row_off(tid);
 #pragma unroll
@@ -214,13 +218,13 @@ __global__ void __launch_bounds__(kTile, kCtasPerSm) field_forward_kernel(const 
     if (args.mode == 0) continue;
 
     // ---- colour net: [SH16 | geo15 | 1.0] -> 64 (ReLU) -> 64 (ReLU) -> 16 -> sigmoid[:3] ----
-    write_color_input(f, sm.a, a_row_off(tid), s, o);
+    write_color_input(f, sm.a, a_row_off(tid), load_view(f, args.s, valid ? i : n), o);
     if (f.color_in_width == 48) run_layer<kSimt, 64, 48>(sm, sm.a, kWCol1, phase, v);
     else run_layer<kSimt, 64, 32>(sm, sm.a, kWCol1, phase, v);
     store_hidden(sm.a, tid, v);
-    run_layer<kSimt, 64, 64>(sm, sm.a, kWCol2, phase, v);
+    run_layer<kSimt, 64, 64>(sm, sm.a, w_col2(f.color_in_width), phase, v);
     store_hidden(sm.a, tid, v);
-    run_layer<kSimt, 16, 64>(sm, sm.a, kWCol3, phase, o);
+    run_layer<kSimt, 16, 64>(sm, sm.a, w_col3(f.color_in_width), phase, o);
     if (valid && args.rgb != nullptr) {
       float* rp = args.rgb + 3 * i;
       rp[0] = 1.f / (1.f + __expf(-o[0]));
@@ -244,7 +248,7 @@ using namespace hrf;
 
 static int launch_field_forward(const FieldArgs& a, int mlp_impl, cudaStream_t st, bool persistent_full) {
   const int64_t tiles = (a.s.num_samples + kTile - 1) / kTile;
-  const int smem = (int)sizeof(FwdSmem) + 128;
+  const int smem = (int)(offsetof(FwdSmem, w) + w_blob_bytes(a.f.color_in_width)) + 128;
   // CTAs per SM, measured on B200 on the bench batch: 4 (118 regs) 1.291 ms, 5 (96 regs) 1.265 ms, 6 (80 regs,
   // spills, less gather ILP per thread) 1.475 ms.  HRF_FWD_CTAS overrides for experiments.
   static const int ctas_per_sm = [] {
@@ -252,7 +256,10 @@ static int launch_field_forward(const FieldArgs& a, int mlp_impl, cudaStream_t s
     const int v = e ? atoi(e) : 5;
     return (v == 4 || v == 6) ? v : 5;
   }();
-  const int64_t max_ctas = (int64_t)sm_count() * ctas_per_sm;
+  static const bool ctas_forced = getenv("HRF_FWD_CTAS") != nullptr;
+  // with camera embeddings the blob is 2 KB larger: 5 CTAs would need the 228 KB carve-out (almost no L1) -> use 4
+  const int ctas = (!ctas_forced && a.f.color_in_width == 48) ? 4 : ctas_per_sm;
+  const int64_t max_ctas = (int64_t)sm_count() * ctas;
   const int grid = (int)((tiles < max_ctas && !persistent_full) ? tiles : max_ctas);
   auto launch = [&](auto kernel) -> int {
     HRF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -261,8 +268,9 @@ static int launch_field_forward(const FieldArgs& a, int mlp_impl, cudaStream_t s
   };
   int rc;
   if (mlp_impl != 0) rc = launch(field_forward_kernel<true, 4>);
-  else if (ctas_per_sm == 6) rc = launch(field_forward_kernel<false, 6>);
-  else if (ctas_per_sm == 4) rc = launch(field_forward_kernel<false, 4>);
+  else if (a.egrid != nullptr) rc = launch(field_forward_kernel<false, 5, true>);   // training forward: also saves e_k
+  else if (ctas == 6) rc = launch(field_forward_kernel<false, 6>);
+  else if (ctas == 4) rc = launch(field_forward_kernel<false, 4>);
   else rc = launch(field_forward_kernel<false, 5>);
   if (rc) return rc;
   HRF_CHECK_LAUNCH();
@@ -289,7 +297,7 @@ static int check_field_args(const hrf_field* f, const hrf_samples* s, int mode) 
 }
 
 extern "C" int hrf_field_forward(const hrf_field* f, const hrf_samples* s, int mode, int mlp_impl, float* sigma,
-                                 void* geo_bf16, float* rgb, void* feat_bf16, void* stream) {
+                                 void* geo_bf16, float* rgb, void* feat_bf16, void* grid_feat_bf16, void* stream) {
   if (int rc = check_field_args(f, s, mode)) return rc;
   if (s->num_samples == 0) return 0;
   FieldArgs a;
@@ -300,6 +308,7 @@ extern "C" int hrf_field_forward(const hrf_field* f, const hrf_samples* s, int m
   a.geo = reinterpret_cast<uint32_t*>(geo_bf16);
   a.rgb = rgb;
   a.feat = reinterpret_cast<uint4*>(feat_bf16);
+  a.egrid = reinterpret_cast<uint32_t*>(grid_feat_bf16);
   a.mode = mode;
   return launch_field_forward(a, mlp_impl, reinterpret_cast<cudaStream_t>(stream), false);
 }
@@ -342,6 +351,7 @@ extern "C" int hrf_field_density_early_stop(const hrf_field* f, const hrf_sample
   a.geo = nullptr;
   a.rgb = nullptr;
   a.feat = nullptr;
+  a.egrid = nullptr;
   a.mode = 0;
   ray_max_chunks_kernel<<<(unsigned)((num_rays + 255) / 256), 256, 0, st>>>(ray_offsets, num_rays,
                                                                            reinterpret_cast<int32_t*>(ws + 16));

@@ -51,8 +51,12 @@ class GridLayout:
 # ---- packed bf16 MLP blob (UMMA K-major SWIZZLE_NONE core-matrix layout, csrc/field_common.cuh) ----
 MLP_SIGMA_PARAMS = 64 * 32 + 16 * 64          # 3072  (tcnn FullyFusedMLP, output padded to 16)
 MLP_BLOB_ELEMS = 22528 // 2
-# byte offsets of the five weight matrices inside the blob (kWSig1.. in csrc/field_common.cuh)
-_BLOB_OFFSETS = (0, 4096, 6144, 12288, 20480)
+
+
+def blob_offsets(camera_embedding_dim: int = 0):
+    """Byte offsets of the five weight matrices inside the blob (kWSig1.., w_col2/w_col3 in csrc/field_common.cuh)."""
+    k = color_in_width(camera_embedding_dim)
+    return (0, 4096, 6144, 6144 + 128 * k, 6144 + 128 * k + 8192)
 
 
 def color_in_width(camera_embedding_dim: int) -> int:
@@ -76,7 +80,7 @@ def mlp_blob_permutation(camera_embedding_dim: int = 0):
     """(dst, src): blob_elems[dst] = cat(sigma_params, color_params)[src]; untouched blob elements stay 0."""
     dst, src = [], []
     s0 = 0
-    for (n_out, n_in), off in zip(mlp_layers(camera_embedding_dim), _BLOB_OFFSETS):
+    for (n_out, n_in), off in zip(mlp_layers(camera_embedding_dim), blob_offsets(camera_embedding_dim)):
         n, k = np.meshgrid(np.arange(n_out), np.arange(n_in), indexing="ij")
         d = off // 2 + ((k // 8) * (n_out // 8) + n // 8) * 64 + (n % 8) * 8 + (k % 8)
         dst.append(d.reshape(-1))

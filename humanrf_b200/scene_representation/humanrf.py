@@ -289,15 +289,23 @@ class _NativeField:
         return s
 
     def forward(self, samples: L.Samples, mode: int, want_geo: bool, want_feat: bool, mlp_impl: int = 0):
+        """Returns (sigma, geo, rgb, saved).  `saved` (when want_feat) is ONE flat bf16 buffer of 160 elements per
+        sample: the composed features [N,32] (64 B/sample, `saved_features(saved, n)`), followed by the per-(level,grid)
+        interpolated features [64][N] bf16x2 (256 B/sample) -- everything the backward needs instead of re-gathering."""
         dev = self._device()
         n = int(samples.num_samples)
         sigma = torch.empty(n, dtype=torch.float32, device=dev)
         geo = torch.empty((n, 16), dtype=torch.bfloat16, device=dev) if want_geo else None
         rgb = torch.empty((n, 3), dtype=torch.float32, device=dev) if mode == 1 else None
-        feat = torch.empty((n, 32), dtype=torch.bfloat16, device=dev) if want_feat else None
+        saved = torch.empty(n * 160, dtype=torch.bfloat16, device=dev) if want_feat else None
+        egrid = saved.data_ptr() + 64 * n if (want_feat and n > 0) else None
         L.check(L.lib().hrf_field_forward(C.byref(self.field), C.byref(samples), mode, mlp_impl, sigma.data_ptr(),
-                                          L.ptr(geo), L.ptr(rgb), L.ptr(feat), L.stream()))
-        return sigma, geo, rgb, feat
+                                          L.ptr(geo), L.ptr(rgb), L.ptr(saved), egrid, L.stream()))
+        return sigma, geo, rgb, saved
+
+    @staticmethod
+    def saved_features(saved: torch.Tensor, n: int) -> torch.Tensor:
+        return saved[: n * 32].view(n, 32)
 
     def density_early_stop(self, samples: L.Samples, ray_offsets: torch.Tensor, num_rays: int, step: float,
                            stop_depth: float = 9.4) -> torch.Tensor:
@@ -328,9 +336,11 @@ class _NativeField:
         d_mlp = torch.zeros(m.mlp_grad_elems, dtype=torch.float32, device=dev)
         d_emb = grad_tensors[i + 2] if m.camera_embedding_dim > 0 else None
         ws = torch.empty(int(samples.num_samples) * 40, dtype=torch.float32, device=dev)   # 160 B / sample
+        n = int(samples.num_samples)
+        egrid = feat.data_ptr() + 64 * n if (feat is not None and feat.numel() >= n * 160 and n > 0) else None
         L.check(L.lib().hrf_field_backward(C.byref(self.field), C.byref(samples), sg_dev.data_ptr(), L.ptr(d_sigma),
-                                           L.ptr(d_rgb), L.ptr(feat), d_mlp.data_ptr(), L.ptr(d_emb), ws.data_ptr(),
-                                           L.stream()))
+                                           L.ptr(d_rgb), L.ptr(feat), egrid, d_mlp.data_ptr(), L.ptr(d_emb),
+                                           ws.data_ptr(), L.stream()))
         grad_tensors[i].add_(d_mlp[:MLP_SIGMA_PARAMS])
         grad_tensors[i + 1].add_(d_mlp[MLP_SIGMA_PARAMS:])
         return sg_dev  # keep alive until the kernel has run (stream-ordered free is safe, but be explicit)

@@ -139,8 +139,8 @@ class FusedTrainer:
         self.grad.zero_()
         ws = torch.empty(n * 40, dtype=torch.float32, device=dev)   # 160 B / sample
         L.check(lib.hrf_field_backward(C.byref(nat.field), C.byref(samples), self.sg_dev.data_ptr(), d_sigma.data_ptr(),
-                                       d_rgb.data_ptr(), feat.data_ptr(), self.mlp_grad.data_ptr(), L.ptr(self.emb_grad),
-                                       ws.data_ptr(), L.stream()))
+                                       d_rgb.data_ptr(), feat.data_ptr(), feat.data_ptr() + 64 * n, self.mlp_grad.data_ptr(),
+                                       L.ptr(self.emb_grad), ws.data_ptr(), L.stream()))
         launches += 8 + 12
         mark("backward")
         # ---- data parallel: one all-reduce of the flat bucket (sum), mean over ranks folded into Adam's grad_scale

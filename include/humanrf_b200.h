@@ -150,6 +150,7 @@ typedef struct {
 int hrf_field_forward(const hrf_field* f, const hrf_samples* s, int mode, int mlp_impl,
                       float* sigma /* [N] */, void* geo_bf16 /* [N,16] (col 0 = raw h0) */,
                       float* rgb /* [N,3] */, void* feat_bf16 /* [N,32] composed features saved for backward, or NULL */,
+                      void* grid_feat_bf16 /* [64,N] bf16x2 per-(level,grid) interpolated features for backward, or NULL */,
                       void* stream);
 
 /* Density-only pass of prune_samples (volume_rendering.py:66-84) with an exact early stop: ray chunks are
@@ -201,6 +202,7 @@ typedef struct {
 int hrf_field_backward(const hrf_field* f, const hrf_samples* s, const hrf_segment_grads* seg_grads /* device array */,
                        const float* d_sigma /* [N] */, const float* d_rgb /* [N,3] or NULL */,
                        const void* feat_bf16 /* [N,32] from hrf_field_forward, or NULL to re-encode */,
+                       const void* grid_feat_bf16 /* [64,N] from hrf_field_forward, or NULL to re-gather the tables */,
                        float* d_mlp /* fp32 [3072 + 64*color_in_width + 5120]: sigma W1,W2, colour W1,W2,W3 row-major [out,in] */,
                        float* d_camera_embeddings /* fp32 [num_cameras, dim] accumulated into, or NULL */,
                        void* workspace /* 160 bytes per sample (16-byte aligned): d(features) level-major, positions, segment ids */, void* stream);

@@ -24,7 +24,7 @@ def _oracle_param_list(om):
 
 
 @pytest.mark.parametrize("segs", [(6,), (6, 6)], ids=["1seg", "2seg"])
-@pytest.mark.parametrize("use_saved_features", [True, False])
+@pytest.mark.parametrize("use_saved_features", [True, False, "composed-only"])
 def test_field_backward_matches_autograd(cuda, segs, use_saved_features):
     om, m, frames = make_pair(segs)
     for p in om.parameters():
@@ -43,7 +43,8 @@ def test_field_backward_matches_autograd(cuda, segs, use_saved_features):
     _, _, _, feat = nat.forward(s, 1, want_geo=False, want_feat=True)
     params = m.hot_parameters()
     grads = [torch.zeros_like(p) for p in params]
-    nat.backward(s, d_sigma.to(cuda), d_rgb.to(cuda).contiguous(), feat if use_saved_features else None, grads)
+    saved = {True: feat, False: None, "composed-only": feat[: n * 32].clone()}[use_saved_features]   # full / re-encode / re-gather
+    nat.backward(s, d_sigma.to(cuda), d_rgb.to(cuda).contiguous(), saved, grads)
     torch.cuda.synchronize()
 
     i = 0

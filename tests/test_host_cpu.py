@@ -91,9 +91,10 @@ def test_mlp_blob_permutation():
     dst, src = mlp_blob_permutation(0)
     # element (n=9, k=17) of the first layer [64,32]: core (kg=2, ng=1), row 1, col 1
     assert src[dst.tolist().index((2 * 8 + 1) * 64 + 1 * 8 + 1)] == 9 * 32 + 17
-    # colour W2 starts at byte 12288 whatever the colour input width
+    # colour W2 follows colour W1 [64,K]: byte 6144 + 128*K
     dst48, src48 = mlp_blob_permutation(2)
-    assert dst48[src48.tolist().index(3072 + 64 * 48)] == 12288 // 2
+    assert dst48[src48.tolist().index(3072 + 64 * 48)] == (6144 + 128 * 48) // 2
+    assert dst[src.tolist().index(3072 + 64 * 32)] == (6144 + 128 * 32) // 2
 
 
 def test_c_abi_exports_every_declared_symbol():
