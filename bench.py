@@ -240,11 +240,14 @@ def main():
                                           bg.data_ptr(), color.data_ptr(), wsum.data_ptr(), None, L.stream()))
         launches["n"] += 3
 
-    kept = []
+    kept, bwd_ev = [], []
 
     def step_train(ev=None):
-        launches["n"] += trainer.step(g["o"], g["d"], g["frames"], g["t"], g["ri"], g["rgba"], RAYS, kernel_event=ev)
+        be = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        launches["n"] += trainer.step(g["o"], g["d"], g["frames"], g["t"], g["ri"], g["rgba"], RAYS, kernel_event=ev,
+                                      bwd_events=be)
         kept.append(trainer.last["samples"])
+        bwd_ev.append(be)
 
     step = step_render if args.mode == "render" else step_train
 
@@ -318,8 +321,16 @@ def main():
     if rank == 0:
         value = world * RAYS * args.steps / (total_ms * 1e-3)
         peak, which = load_peaks()
-        alg_bytes = ALG_BYTES_FWD * n if args.mode == "render" else 12300 * n
-        achieved = alg_bytes / (kern_ms * 1e-3) / 1e9 if args.mode == "render" else alg_bytes / (total_ms / args.steps * 1e-3) / 1e9
+        if args.mode == "render":
+            alg_per_sample, roof_kernel = ALG_BYTES_FWD, "field_forward_kernel"
+            achieved = alg_per_sample * n / (kern_ms * 1e-3) / 1e9
+        else:
+            # dominant kernels of the train step: field_backward_kernel + grid_scatter_kernel over the pruned samples.
+            # SURVEY 8d convention for the backward: table-gradient RMW 2 x 2048 B + vector-gradient RMW 2 x 1024 B +
+            # re-read of tables / vectors 3072 B = 9216 B per sample.
+            alg_per_sample, roof_kernel = 9216, "field_backward_kernel + grid_scatter_kernel"
+            kern_ms = sum(a.elapsed_time(b) for a, b in bwd_ev[-args.steps:]) / args.steps
+            achieved = alg_per_sample * (sum(kept[-args.steps:]) / args.steps) / (kern_ms * 1e-3) / 1e9
         line = {
             "metric": METRIC[args.mode], "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -339,9 +350,8 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one field_forward_kernel launch on this very batch,
                          # from the committed ncu --set full capture (profiles/r1_ncu_full_fwd_raw.csv)
-                         "traffic": 118.8e6 if args.mode == "render" else None, "traffic_unit": "bytes/launch",
-                         "peak_source": which, "kernel": "field_forward_kernel" if args.mode == "render" else "train step",
-                         "kernel_ms": kern_ms, "algorithmic_bytes_per_sample": ALG_BYTES_FWD if args.mode == "render" else 12300},
+                         "traffic": 130.0e6 if args.mode == "render" else None, "traffic_unit": "bytes/launch",
+                         "peak_source": which, "kernel": roof_kernel, "kernel_ms": kern_ms, "algorithmic_bytes_per_sample": alg_per_sample},
             "wall_s_timed_loop": t_wall,
         }
         if world == 1 and not args.no_cpu_baseline:

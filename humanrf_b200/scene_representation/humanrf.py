@@ -117,15 +117,19 @@ class HumanRF(torch.nn.Module):
     # ------------------------------------------------------------------ reference API
     def density(self, query_input: QueryInput) -> QueryOutput:
         sigma, geo, _ = _FieldFunction.apply(self, 0, query_input.positions, None, query_input.frame_numbers, None,
-                                             *self.hot_parameters())
+                                             self._needs_grad(), *self.hot_parameters())
         return QueryOutput(density=sigma, geometry_features=geo)
 
     def forward(self, query_input: QueryInput) -> QueryOutput:
         # humanrf.py:194-204: the camera embedding is looked up while training and is all zeros otherwise
         cams = query_input.camera_numbers if (self.camera_embedding_dim > 0 and query_input.is_training) else None
         sigma, geo, rgb = _FieldFunction.apply(self, 1, query_input.positions, query_input.directions,
-                                               query_input.frame_numbers, cams, *self.hot_parameters())
+                                               query_input.frame_numbers, cams, self._needs_grad(), *self.hot_parameters())
         return QueryOutput(density=sigma, geometry_features=geo, radiance=rgb)
+
+    def _needs_grad(self) -> bool:
+        # ctx.needs_input_grad ignores torch.no_grad(); decide outside whether to save the backward buffers
+        return torch.is_grad_enabled() and any(p.requires_grad for p in self.hot_parameters())
 
     def get_params(self, lr):
         params = [
@@ -358,13 +362,12 @@ class _FieldFunction(torch.autograd.Function):
     """autograd wrapper of the fused kernels in QueryInput form (humanrf.py:158-208)."""
 
     @staticmethod
-    def forward(ctx, model: HumanRF, mode: int, positions, directions, frame_numbers, camera_numbers, *params):
+    def forward(ctx, model: HumanRF, mode: int, positions, directions, frame_numbers, camera_numbers, needs_grad, *params):
         nat = model.native()
         pos = L.require_cuda(_as_f32c(positions), "positions")
         dirs = None if directions is None else L.require_cuda(_as_f32c(directions), "directions")
         frames = L.require_cuda(_as_frames(frame_numbers), "frame_numbers")
         cams = None if camera_numbers is None else L.require_cuda(_as_frames(camera_numbers), "camera_numbers")
-        needs_grad = any(ctx.needs_input_grad[6:])
         samples = nat.samples_query(pos, dirs, frames, cams)
         sigma, geo, rgb, feat = nat.forward(samples, mode, want_geo=True, want_feat=needs_grad)
         ctx.model, ctx.mode = model, mode
@@ -392,4 +395,4 @@ class _FieldFunction(torch.autograd.Function):
             ds = torch.zeros(pos.shape[0], dtype=torch.float32, device=pos.device)
         keep = nat.backward(samples, ds, dr, feat, grads)
         del keep
-        return (None, None, None, None, None, None, *grads)
+        return (None, None, None, None, None, None, None, *grads)

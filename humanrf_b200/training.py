@@ -68,7 +68,7 @@ class FusedTrainer:
         return self.lr * self.lr_decay ** min(self.t / self.max_steps, 1.0)  # run.py:102-104
 
     def step(self, o, d, frames, t, ri, rgba, num_rays: int, kernel_event=None, return_loss: bool = False,
-             background: Optional[torch.Tensor] = None, cameras: Optional[torch.Tensor] = None):
+             background: Optional[torch.Tensor] = None, cameras: Optional[torch.Tensor] = None, bwd_events=None):
         """One optimisation step on a ray batch given in InputBatch layout (device tensors).
         Returns the number of kernels launched, or the loss value when return_loss."""
         lib, nat, dev = L.lib(), self.model.native(), t.device
@@ -137,10 +137,14 @@ class FusedTrainer:
                                            bg.data_ptr(), color.grad.data_ptr(), wsum.grad.reshape(-1).data_ptr(),
                                            d_sigma.data_ptr(), d_rgb.data_ptr(), L.stream()))
         self.grad.zero_()
+        if bwd_events is not None:
+            bwd_events[0].record()
         ws = torch.empty(n * 40, dtype=torch.float32, device=dev)   # 160 B / sample
         L.check(lib.hrf_field_backward(C.byref(nat.field), C.byref(samples), self.sg_dev.data_ptr(), d_sigma.data_ptr(),
                                        d_rgb.data_ptr(), feat.data_ptr(), feat.data_ptr() + 64 * n, self.mlp_grad.data_ptr(),
                                        L.ptr(self.emb_grad), ws.data_ptr(), L.stream()))
+        if bwd_events is not None:
+            bwd_events[1].record()
         launches += 8 + 12
         mark("backward")
         # ---- data parallel: one all-reduce of the flat bucket (sum), mean over ranks folded into Adam's grad_scale

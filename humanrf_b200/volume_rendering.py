@@ -87,10 +87,9 @@ class _RenderFunction(torch.autograd.Function):
     """field forward (ray-batch form) + compositing; backward = composite bwd + fused field bwd."""
 
     @staticmethod
-    def forward(ctx, model: HumanRF, o, d, fr, t, ri, num_rays, background, step, cams, *params):
+    def forward(ctx, model: HumanRF, o, d, fr, t, ri, num_rays, background, step, cams, needs_grad, *params):
         nat = model.native()
         dev = t.device
-        needs_grad = any(ctx.needs_input_grad[10:])
         samples = nat.samples_rays(o, d, fr, t, ri, cams)
         sigma, _, rgb, feat = nat.forward(samples, 1, want_geo=False, want_feat=needs_grad)
         off = ray_offsets(ri, num_rays)
@@ -127,7 +126,7 @@ class _RenderFunction(torch.autograd.Function):
         params = model.hot_parameters()
         grads = [torch.zeros_like(p) for p in params]
         nat.backward(nat.samples_rays(o, d, fr, t, ri, cams if ctx.has_cams else None), d_sigma, d_rgb, feat, grads)
-        return (None,) * 10 + tuple(grads)
+        return (None,) * 11 + tuple(grads)
 
 
 def render(input_batch: InputBatch, scene_representation: HumanRF, background_rgb: torch.Tensor, is_training: bool,
@@ -138,6 +137,9 @@ def render(input_batch: InputBatch, scene_representation: HumanRF, background_rg
     cams = None
     if scene_representation.camera_embedding_dim > 0 and is_training:   # humanrf.py:194-204 (zeros at evaluation)
         cams = L.require_cuda(ib.camera_numbers.detach().reshape(-1).to(torch.int32).contiguous(), "camera_numbers")
+    params = scene_representation.hot_parameters()
+    # (ctx.needs_input_grad ignores torch.no_grad(): decide here whether the backward buffers are worth saving)
+    needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
     color, wsum = _RenderFunction.apply(scene_representation, o, d, fr, t, ri, ib.num_rays, background_rgb,
-                                        render_step_size, cams, *scene_representation.hot_parameters())
+                                        render_step_size, cams, needs_grad, *params)
     return RenderOutput(color=color, weights_sum=wsum)
