@@ -30,15 +30,15 @@ def deal_round_robin(items: Sequence, rank: int, world: int) -> List:
     return [x for i, x in enumerate(items) if i % world == rank]
 
 
-def union_batch_loss_scale(num_rays_local: int, device, group=None) -> float:
+def union_batch_loss_scale(num_rays_local: int, device, group=None):
     """world * R_local / R_total, so that summing rank gradients and dividing by world gives the gradient of the
-    mean loss over the union of all ranks' rays.  One 8-byte all-reduce."""
+    mean loss over the union of all ranks' rays.  One 8-byte all-reduce; the result stays ON THE DEVICE (a 0-dim
+    tensor to multiply the loss with), so the step keeps running without a host sync."""
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return 1.0
-    t = torch.tensor([float(num_rays_local)], dtype=torch.float64, device=device)
+    t = torch.full((1,), float(num_rays_local), dtype=torch.float32, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
-    total = float(t.item())
-    return dist.get_world_size(group) * num_rays_local / total if total > 0 else 0.0
+    return (dist.get_world_size(group) * float(num_rays_local)) / t.clamp(min=1.0)[0]
 
 
 def allreduce_bucket_(flat: torch.Tensor, group=None) -> torch.Tensor:
