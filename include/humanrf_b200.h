@@ -230,6 +230,20 @@ int hrf_adam_step(float* param, float* exp_avg, float* exp_avg_sq, const float* 
 int hrf_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Pre-processing that feeds the hot path.
+ * hrf_occupancy_from_masks: visual-hull carving, replaces occupancy_grid_generation_native.generate_from_masks
+ * (actorshq/toolbox/native/occupancy_grid_generation.cu:16-123).  projection_matrices [C,4,4] are stored transposed
+ * exactly as the reference passes them (GLM is column-major).
+ * hrf_occupancy_union_count: cluster |= (grid == 255); *count_dev = popcount(cluster) -- equations (2)-(4) of
+ * humanrf/adaptive_temporal_partitioning.py:11-26 on a bit-packed union (grid_u8 may be NULL to only count).
+ * ---------------------------------------------------------------------------------------- */
+int hrf_occupancy_from_masks(const uint8_t* masks /* [C, H*W] */, const float* projection_matrices /* [C,4,4] */,
+                             const uint8_t* landscape_modes /* [C] bool */, int num_cameras, int camera_coverage_threshold,
+                             int grid_resolution, int width, int height, uint8_t* occupancy_grid /* [G,G,G] */, void* stream);
+int hrf_occupancy_union_count(void* cluster_bits /* ceil(n/32) u32, caller-zeroed per cluster */, const uint8_t* grid_u8 /* [n] */,
+                              int64_t num_voxels, int64_t* count_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Self tests (used by tests/ only): one 128xN x K tcgen05 MMA with caller-chosen descriptor
  * fields, to pin the shared-memory descriptor encoding on real hardware.
  * ---------------------------------------------------------------------------------------- */

@@ -5,6 +5,7 @@ box can diff our kernels against the real thing:
   tensor_composition_native  <- humanrf/scene_representation/native/tensor_composition.cu
   occupancy_grid_native      <- actorshq/dataset/native/occupancy_grid.cu
   ray_sampler_native         <- actorshq/dataset/native/ray_sampler.cu   (+ oracle/glm_shim: GLM is absent here)
+  occupancy_grid_generation_native <- actorshq/toolbox/native/occupancy_grid_generation.cu   (+ oracle/glm_shim)
 
 Flags follow humanrf/setup.py:17 and actorshq/setup.py:17-29 (--use_fast_math) with the arch
 pinned to sm_100.  tinycudann / nerfacc are not under /root/reference and cannot be built.
@@ -25,6 +26,7 @@ EXTS = {
     "tensor_composition_native": (REF / "humanrf/scene_representation/native/tensor_composition.cu", []),
     "occupancy_grid_native": (REF / "actorshq/dataset/native/occupancy_grid.cu", []),
     "ray_sampler_native": (REF / "actorshq/dataset/native/ray_sampler.cu", [HERE / "glm_shim"]),
+    "occupancy_grid_generation_native": (REF / "actorshq/toolbox/native/occupancy_grid_generation.cu", [HERE / "glm_shim"]),
 }
 
 

@@ -114,3 +114,55 @@ class SyntheticDataset:
 
     def get_occupancy_grid(self, frame_number):
         return self._grids[frame_number]
+
+
+def occupancy_sequence(n, speed, G=48, seed=0):
+    """n occupancy grids of a drifting ellipsoid pair (speed = drift per frame; None = static with sudden jumps), the
+    input of adaptive temporal partitioning."""
+    rng = np.random.default_rng(seed)
+    c = (np.arange(G) + 0.5) / G - 0.5
+    z, y, x = np.meshgrid(c, c, c, indexing="ij")
+    ctr = rng.uniform(-0.1, 0.1, (2, 3))
+    rad = rng.uniform(0.1, 0.2, (2, 3))
+    vel = rng.normal(size=(2, 3))
+    vel /= np.linalg.norm(vel, axis=1, keepdims=True)
+    grids = []
+    for f in range(n):
+        occ = np.zeros((G, G, G), bool)
+        for k in range(2):
+            if speed is None:
+                p = ctr[k] + 0.12 * vel[k] * ((f // 37) % 3)
+            else:
+                p = ctr[k] + speed * f * vel[k] * np.cos(0.05 * f)
+            occ |= ((x - p[0]) / rad[k, 0]) ** 2 + ((y - p[1]) / rad[k, 1]) ** 2 + ((z - p[2]) / rad[k, 2]) ** 2 <= 1.0
+        grids.append((occ * 255).astype(np.uint8))
+    return grids
+
+
+def carve_scene(num_cameras=12, width=96, height=72, seed=0, portrait_every=4):
+    """Foreground masks of an ellipsoid union seen from a camera ring + the transposed world2pixel matrices, the input
+    of generate_from_masks (generate_occupancy_grids_from_masks.py:44-93)."""
+    rng = np.random.default_rng(seed)
+    ctr = rng.uniform(-0.12, 0.12, (3, 3))
+    rad = rng.uniform(0.08, 0.22, (3, 3))
+    masks = np.zeros((num_cameras, width * height), np.uint8)
+    mats, land = [], []
+    for i in range(num_cameras):
+        a = 2 * np.pi * i / num_cameras + 0.2
+        pos = np.array([2.0 * np.cos(a), rng.uniform(-0.5, 0.5), 2.0 * np.sin(a)])
+        ls = not (portrait_every and i % portrait_every == portrait_every - 1)
+        w, h = (width, height) if ls else (height, width)
+        M = look_at_camera(pos, w, h)
+        ikr = inverse_kr(M)
+        u, v = np.meshgrid(np.arange(w) + 0.5, np.arange(h) + 0.5)
+        d = np.stack([u, v, np.ones_like(u)], -1) @ np.asarray(ikr, np.float64)      # inverse_kr is stored transposed
+        d /= np.linalg.norm(d, axis=-1, keepdims=True)
+        hit = np.zeros((h, w), bool)
+        for k in range(3):                                      # ray / ellipsoid intersection
+            o_, d_ = (pos - ctr[k]) / rad[k], d / rad[k]
+            A, B, Cc = (d_ * d_).sum(-1), 2 * (d_ * o_).sum(-1), (o_ * o_).sum() - 1
+            hit |= B * B - 4 * A * Cc >= 0
+        masks[i] = (hit * 255).astype(np.uint8).reshape(-1)
+        mats.append(np.asarray(M, np.float32).T.copy())          # transposed, as the reference passes them to GLM
+        land.append(ls)
+    return dict(masks=masks, projection_matrices=np.stack(mats), landscape=np.array(land), width=width, height=height)
