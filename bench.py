@@ -55,7 +55,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:  # noqa: BLE001
             self.proc = None
 
@@ -256,11 +256,11 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local)   # samples every 20 ms from the warm-up to the end of the e2e loop: the GPU is under load throughout
     for _ in range(max(args.warmup, 3)):
         flush.zero_()
         step()
     barrier()
-    clocks = ClockSampler(local)
     launches["n"] = 0
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     t_wall = time.perf_counter()
@@ -271,7 +271,6 @@ def main():
         ev[i][2].record()
     barrier()
     t_wall = time.perf_counter() - t_wall
-    clk = clocks.stop()
     step_ms = sum(e[0].elapsed_time(e[2]) for e in ev)
     kern_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
     tt = torch.tensor([step_ms], device=dev, dtype=torch.float64)
@@ -288,12 +287,13 @@ def main():
 
     from humanrf_b200.dataset.input_batch import InputBatch
 
-    # Render: two steps in flight on two streams, so step i+1's H2D copy and step i-1's D2H read overlap step i's
+    # Render: three steps in flight on three streams (one pinned->device stream sustains ~16 GB/s on this host, scripts/e2e_probe.py), so step i+1's H2D copy and step i-1's D2H read overlap step i's
     # kernels (copy engines beside the SMs) -- how a renderer walks the tiles of an image.  Train: steps are
     # sequentially dependent (Adam), so only the next batch's H2D copy is prefetched on a copy stream.  Every step's
     # copies are issued, and complete, inside the timed region.
-    streams = [torch.cuda.Stream(dev) for _ in range(2)]
-    host_colors = [host_color, torch.empty(RAYS, 3).pin_memory()]
+    DEPTH = 3
+    streams = [torch.cuda.Stream(dev) for _ in range(DEPTH)]
+    host_colors = [host_color] + [torch.empty(RAYS, 3).pin_memory() for _ in range(DEPTH - 1)]
     keys = ("o", "d", "frames", "t", "ri") if args.mode == "render" else ("o", "d", "frames", "t", "ri", "rgba")
 
     def upload(stream):
@@ -305,13 +305,13 @@ def main():
 
     def e2e_render(k):
         for i in range(k):
-            st = streams[i % 2]
+            st = streams[i % DEPTH]
             bb, _ = upload(st)
             with torch.cuda.stream(st), torch.no_grad():
                 ib = InputBatch(ray_origins=bb["o"], ray_directions=bb["d"], frame_numbers=bb["frames"].view(-1, 1),
                                 sample_distances=bb["t"].view(-1, 1), ray_indices=bb["ri"])
                 out = render(ib, model, bg, is_training=False)
-                host_colors[i % 2].copy_(out.color, non_blocking=True)
+                host_colors[i % DEPTH].copy_(out.color, non_blocking=True)
         torch.cuda.synchronize()
 
     def e2e_train(k):
@@ -329,10 +329,12 @@ def main():
     e2e_loop(3)
     barrier()
     t0 = time.perf_counter()
-    k_e2e = max(4, args.steps // 2)
+    k_e2e = max(6, args.steps // 2)
     e2e_loop(k_e2e)
     barrier()
     e2e_s = time.perf_counter() - t0
+    clk = clocks.stop()
+    clk["window"] = "warm-up + timed steps + e2e loop"
     te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -368,7 +370,7 @@ def main():
                           if args.mode == "train" else {})},
             "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "api": "humanrf_b200.volume_rendering.render" if args.mode == "render" else "humanrf_b200.training.FusedTrainer.step",
-                    "pipelining": "2 steps in flight on 2 streams" if args.mode == "render" else "next batch's H2D prefetched on a copy stream"},
+                    "pipelining": "3 steps in flight on 3 streams" if args.mode == "render" else "next batch's H2D prefetched on a copy stream"},
             "gpu_launches": gpu_launches,
             "clocks": clk,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -147,6 +147,7 @@ struct ScatterArgs {
   const float4* pos4;   // [N] (x,y,z,t), written by field_backward_kernel
   const uint8_t* seg8;  // [N]
   const uint32_t* egrid;  // bf16x2 [16*4][N] per-grid features saved by the forward, or NULL (re-gather the tables)
+  int grid_first, grid_count;  // this launch covers grids [grid_first, grid_first + grid_count) of xyz, xyt, yzt, xzt
 };
 
 __global__ void __launch_bounds__(256, 3) grid_scatter_kernel(const __grid_constant__ ScatterArgs a) {
@@ -154,7 +155,7 @@ __global__ void __launch_bounds__(256, 3) grid_scatter_kernel(const __grid_const
   const int64_t n = a.s.num_samples;
   const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * kChunk;
   if (i0 >= n) return;
-  const int l = blockIdx.y >> 2, k = blockIdx.y & 3;
+  const int l = (int)blockIdx.y / a.grid_count, k = a.grid_first + (int)blockIdx.y % a.grid_count;
   const int axis = (k == 0) ? 3 : (k == 1) ? 2 : (k == 2) ? 0 : 1;  // vector axis paired with grid k
   const float scale = f.level_scale[l];
   const uint32_t res = f.level_res[l];
@@ -441,11 +442,10 @@ __global__ void __launch_bounds__(kTile, 2) field_backward_kernel(const __grid_c
 
 using namespace hrf;
 
-extern "C" int hrf_field_backward(const hrf_field* f, const hrf_samples* s, const hrf_segment_grads* seg_grads,
-                                  const float* d_sigma, const float* d_rgb, const void* feat_bf16,
-                                  const void* grid_feat_bf16, float* d_mlp, float* d_camera_embeddings, void* workspace,
-                                  void* stream) {
-  HRF_REQUIRE(f != nullptr && s != nullptr && seg_grads != nullptr, "null argument");
+extern "C" int hrf_field_backward_mlp(const hrf_field* f, const hrf_samples* s, const float* d_sigma, const float* d_rgb,
+                                      const void* feat_bf16, float* d_mlp, float* d_camera_embeddings, void* workspace,
+                                      void* stream) {
+  HRF_REQUIRE(f != nullptr && s != nullptr, "null argument");
   HRF_REQUIRE(f->num_segments < 255, "at most 254 temporal segments");
   if (s->num_samples == 0) return 0;
   HRF_REQUIRE(workspace != nullptr, "hrf_field_backward needs a workspace of 160 bytes per sample");
@@ -454,11 +454,10 @@ extern "C" int hrf_field_backward(const hrf_field* f, const hrf_samples* s, cons
     HRF_REQUIRE(s->positions && s->frame_numbers, "query form needs positions and frame numbers");
     HRF_REQUIRE(d_rgb == nullptr || s->directions, "radiance gradients need directions");
   }
-  if (s->num_samples == 0) return 0;
   BwdArgs a;
   a.f = *f;
   a.s = *s;
-  a.seg_grads = seg_grads;
+  a.seg_grads = nullptr;
   a.d_sigma = d_sigma;
   a.d_rgb = d_rgb;
   a.feat_in = reinterpret_cast<const uint4*>(feat_bf16);
@@ -472,21 +471,40 @@ extern "C" int hrf_field_backward(const hrf_field* f, const hrf_samples* s, cons
   const int64_t max_ctas = (int64_t)sm_count() * 2;
   const int grid = (int)(tiles < max_ctas ? tiles : max_ctas);
   HRF_CUDA(cudaFuncSetAttribute(field_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  field_backward_kernel<<<grid, kTile, smem, st>>>(a);
+  field_backward_kernel<<<grid, kTile, smem, reinterpret_cast<cudaStream_t>(stream)>>>(a);
   HRF_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int hrf_field_backward_tables(const hrf_field* f, const hrf_samples* s, const hrf_segment_grads* seg_grads,
+                                         const void* grid_feat_bf16, const void* workspace, int grid_first, int grid_count,
+                                         void* stream) {
+  HRF_REQUIRE(f != nullptr && s != nullptr && seg_grads != nullptr, "null argument");
+  HRF_REQUIRE(grid_first >= 0 && grid_count >= 1 && grid_first + grid_count <= 4, "grids are 0..3 (xyz, xyt, yzt, xzt)");
+  if (s->num_samples == 0) return 0;
+  HRF_REQUIRE(workspace != nullptr, "needs the workspace hrf_field_backward_mlp filled");
   ScatterArgs sa;
   sa.f = *f;
   sa.s = *s;
   sa.seg_grads = seg_grads;
-  sa.dfeat = a.dfeat;
-  sa.pos4 = a.pos4;
-  sa.seg8 = a.seg8;
+  sa.dfeat = reinterpret_cast<const float2*>(workspace);
+  sa.pos4 = reinterpret_cast<const float4*>(reinterpret_cast<const char*>(workspace) + 128 * (size_t)s->num_samples);
+  sa.seg8 = reinterpret_cast<const uint8_t*>(reinterpret_cast<const char*>(workspace) + 144 * (size_t)s->num_samples);
   sa.egrid = reinterpret_cast<const uint32_t*>(grid_feat_bf16);
-  {
-    const int64_t chunks = (s->num_samples + kChunk - 1) / kChunk;
-    grid_scatter_kernel<<<dim3((unsigned)((chunks + 255) / 256), HRF_N_LEVELS * 4), 256, 0, st>>>(sa);
-  }
+  sa.grid_first = grid_first;
+  sa.grid_count = grid_count;
+  const int64_t chunks = (s->num_samples + kChunk - 1) / kChunk;
+  grid_scatter_kernel<<<dim3((unsigned)((chunks + 255) / 256), HRF_N_LEVELS * grid_count), 256, 0,
+                        reinterpret_cast<cudaStream_t>(stream)>>>(sa);
   HRF_CHECK_LAUNCH();
   return 0;
+}
+
+extern "C" int hrf_field_backward(const hrf_field* f, const hrf_samples* s, const hrf_segment_grads* seg_grads,
+                                  const float* d_sigma, const float* d_rgb, const void* feat_bf16,
+                                  const void* grid_feat_bf16, float* d_mlp, float* d_camera_embeddings, void* workspace,
+                                  void* stream) {
+  HRF_REQUIRE(seg_grads != nullptr, "null argument");
+  if (int rc = hrf_field_backward_mlp(f, s, d_sigma, d_rgb, feat_bf16, d_mlp, d_camera_embeddings, workspace, stream)) return rc;
+  return hrf_field_backward_tables(f, s, seg_grads, grid_feat_bf16, workspace, 0, 4, stream);
 }

@@ -37,10 +37,11 @@ __global__ void __launch_bounds__(256) carve_kernel(const __grid_constant__ Carv
   }
   for (int i = threadIdx.x; i < a.num_cameras; i += blockDim.x) s_ls[i] = a.landscape[i];
   __syncthreads();
-  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int G = a.G;
-  if (v >= (int64_t)G * G * G) return;
-  const int gx = (int)(v % G), gy = (int)((v / G) % G), gz = (int)(v / ((int64_t)G * G));
+  const uint32_t G = (uint32_t)a.G, n = G * G * G;   // G <= 1024 (host check): 32-bit index arithmetic
+  const uint8_t* __restrict__ masks = a.masks;
+  // persistent CTAs: the staging above is paid once per CTA, not once per 256 voxels
+  for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
+  const uint32_t gx = v % G, gyz = v / G, gy = gyz % G, gz = gyz / G;
   const float inv = (float)(G - 1);
   const float x = __fsub_rn(__fdiv_rn((float)gx, inv), 0.5f), y = __fsub_rn(__fdiv_rn((float)gy, inv), 0.5f),
               z = __fsub_rn(__fdiv_rn((float)gz, inv), 0.5f);
@@ -58,8 +59,9 @@ __global__ void __launch_bounds__(256) carve_kernel(const __grid_constant__ Carv
     const int ix = trunc_div(px, pz), iy = trunc_div(py, pz);   // C truncation, as the reference
     if (ix >= 0 && ix < cw && iy >= 0 && iy < ch) {
       const int ix1 = min(ix + 1, cw - 1), iy1 = min(iy + 1, ch - 1);
-      const uint8_t* mk = a.masks + (size_t)c * a.width * a.height;
-      if (mk[ix + iy * cw] == 0 && mk[ix1 + iy * cw] == 0 && mk[ix + iy1 * cw] == 0 && mk[ix1 + iy1 * cw] == 0) {
+      const uint8_t* mk = masks + (size_t)c * a.width * a.height;
+      if (__ldg(mk + ix + iy * cw) == 0 && __ldg(mk + ix1 + iy * cw) == 0 && __ldg(mk + ix + iy1 * cw) == 0 &&
+          __ldg(mk + ix1 + iy1 * cw) == 0) {
         if (covered + (a.num_cameras - c - 1) < a.threshold) break;
       } else {
         ++covered;
@@ -69,6 +71,7 @@ __global__ void __launch_bounds__(256) carve_kernel(const __grid_constant__ Carv
     }
   }
   a.grid[v] = in_hull ? 255 : 0;
+  }
 }
 
 // cluster |= (grid == 255), count = popcount(cluster): the cluster is a bit-packed union of occupancy grids.
@@ -92,12 +95,13 @@ extern "C" int hrf_occupancy_from_masks(const uint8_t* masks, const float* proje
                                         int num_cameras, int camera_coverage_threshold, int grid_resolution, int width,
                                         int height, uint8_t* occupancy_grid, void* stream) {
   HRF_REQUIRE(masks && projection_matrices && landscape_modes && occupancy_grid, "null argument");
-  HRF_REQUIRE(num_cameras > 0 && grid_resolution > 1 && width > 0 && height > 0, "bad sizes");
+  HRF_REQUIRE(num_cameras > 0 && grid_resolution > 1 && grid_resolution <= 1024 && width > 0 && height > 0, "bad sizes");
   HRF_REQUIRE(num_cameras <= kMaxCarveCameras, "at most 160 cameras (the reference's kMaxNumCameras)");
   CarveArgs a{masks, projection_matrices, landscape_modes, camera_coverage_threshold, num_cameras, grid_resolution, width,
               height, occupancy_grid};
   const int64_t n = (int64_t)grid_resolution * grid_resolution * grid_resolution;
-  carve_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  const int64_t want = (n + 255) / 256, cap = (int64_t)sm_count() * 8;
+  carve_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
   HRF_CHECK_LAUNCH();
   return 0;
 }

@@ -41,11 +41,14 @@ def union_batch_loss_scale(num_rays_local: int, device, group=None):
     return (dist.get_world_size(group) * float(num_rays_local)) / t.clamp(min=1.0)[0]
 
 
-def allreduce_bucket_(flat: torch.Tensor, group=None) -> torch.Tensor:
-    """In-place sum of the flat gradient bucket over the ranks (mean is folded into Adam's grad_scale)."""
+def allreduce_bucket_(flat: torch.Tensor, group=None, async_op: bool = False):
+    """In-place sum of (a region of) the flat gradient bucket over the ranks (mean is folded into Adam's grad_scale).
+    With async_op the NCCL work handle is returned (None when there is nothing to reduce): the collective runs on
+    NCCL's stream behind everything already queued on the current stream, and .wait() orders later kernels after it."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    return flat
+        work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+        return work if async_op else flat
+    return None if async_op else flat
 
 
 def broadcast_parameters_(params, src: int = 0, group=None) -> None:

@@ -3,9 +3,9 @@ data-parallel driver).  Same maths as the reference's Trainer.train_step (humanr
 random background, Huber(delta=0.01) + 1e-3 * BCE, Adam lr 1e-2 betas (0.9,0.99) eps 1e-15,
 lr * lr_decay^(min(step/max,1)), run.py:101-104), but:
 
-* gradients are written by the fused backward kernel straight into ONE flat fp32 bucket (no per-parameter
-  zero-filled tensors, no autograd graph), which is also the single NCCL all-reduce message under data
-  parallelism (SURVEY 8e);
+* gradients are written by the fused backward kernels straight into ONE flat fp32 bucket (no per-parameter
+  zero-filled tensors, no autograd graph), laid out grid-major so that under data parallelism the bucket
+  is reduced in 5 NCCL messages, each overlapping the scatter of the next table and the Adam of the previous one;
 * Adam is one fused kernel per parameter that also refreshes the bf16 shadow table the forward reads;
 * bf16 needs no GradScaler, so the inf-check host sync of trainer.py:250-252 disappears.
 
@@ -30,36 +30,49 @@ class FusedTrainer:
     def __init__(self, model: HumanRF, lr: float = 1e-2, betas=(0.9, 0.99), eps: float = 1e-15, lr_decay: float = 0.5,
                  max_steps: int = 50001, bce_loss_weight: float = 1e-3, huber_delta: float = 0.01,
                  render_step_size: float = 4e-4, world_size: int = 1, process_group=None, prune: bool = True,
-                 seed: int = 123):
+                 seed: int = 123, overlap_allreduce: bool = True):
         self.model, self.lr, self.betas, self.eps = model, lr, betas, eps
         self.lr_decay, self.max_steps = lr_decay, max_steps
         self.bce_w, self.delta, self.step_size = bce_loss_weight, huber_delta, render_step_size
         self.world, self.pg, self.prune = world_size, process_group, prune
+        self.overlap_allreduce = overlap_allreduce
         self.params: List[torch.nn.Parameter] = model.hot_parameters()
         dev = self.params[0].device
-        sizes = [p.numel() for p in self.params]
-        self.offsets = np.concatenate(([0], np.cumsum(sizes))).tolist()
-        total = self.offsets[-1]
+        m = model
+        S = m.num_segments
+        # Bucket layout, GRID-MAJOR: [grid 0 of every segment | grid 1 ... | grid 2 ... | grid 3 ... | vectors of every
+        # segment, MLPs, camera embeddings].  Region k is complete as soon as the scatter launch of grid k has run, so under
+        # data parallelism its all-reduce overlaps the scatter of grid k+1 (hot_parameters() itself is segment-major).
+        order = [5 * s_ + k for k in range(4) for s_ in range(S)] + [5 * s_ + 4 for s_ in range(S)] + \
+            list(range(5 * S, len(self.params)))
+        self.slices = [None] * len(self.params)
+        pos = 0
+        self.regions = []
+        for j, i in enumerate(order):
+            if j % S == 0 and j <= 4 * S:
+                self.regions.append(pos)
+            self.slices[i] = (pos, pos + self.params[i].numel())
+            pos = self.slices[i][1]
+        total = pos
+        self.regions = [(a, b) for a, b in zip(self.regions, self.regions[1:] + [total])]     # 4 table regions + the tail
+        self.adam_order = order
         self.grad = torch.zeros(total, dtype=torch.float32, device=dev)       # the all-reduce bucket
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
-        self.grad_views = [self.grad[a:b] for a, b in zip(self.offsets[:-1], self.offsets[1:])]
+        self.grad_views = [self.grad[a:b] for a, b in self.slices]
         self.t = 0
         self.gen = torch.Generator(device=dev).manual_seed(seed)
         self.nat = model.native()
-        m = model
-        sg = (L.SegmentGrads * m.num_segments)()
-        i = 0
-        for s in range(m.num_segments):
+        sg = (L.SegmentGrads * S)()
+        for s_ in range(S):
             for k in range(4):
-                sg[s].grid[k] = self.grad_views[i].data_ptr()
-                i += 1
-            sg[s].vectors = self.grad_views[i].data_ptr()
-            i += 1
+                sg[s_].grid[k] = self.grad_views[5 * s_ + k].data_ptr()
+            sg[s_].vectors = self.grad_views[5 * s_ + 4].data_ptr()
         self.sg_dev = torch.from_numpy(np.frombuffer(bytes(sg), dtype=np.uint8).copy()).to(dev)
-        self.mlp_grad = self.grad[self.offsets[i]:self.offsets[i + 2]]   # sigma params then colour params, contiguous
+        i = 5 * S
+        self.mlp_grad = self.grad[self.slices[i][0]:self.slices[i + 1][1]]   # sigma params then colour params, contiguous
         assert self.mlp_grad.numel() == model.mlp_grad_elems
-        self.emb_grad = self.grad[self.offsets[i + 2]:] if model.camera_embedding_dim > 0 else None
+        self.emb_grad = self.grad_views[i + 2] if model.camera_embedding_dim > 0 else None
         self.last = {}
         self.profile = False
 
@@ -140,18 +153,31 @@ class FusedTrainer:
         if bwd_events is not None:
             bwd_events[0].record()
         ws = torch.empty(n * 40, dtype=torch.float32, device=dev)   # 160 B / sample
-        L.check(lib.hrf_field_backward(C.byref(nat.field), C.byref(samples), self.sg_dev.data_ptr(), d_sigma.data_ptr(),
-                                       d_rgb.data_ptr(), feat.data_ptr(), feat.data_ptr() + 64 * n, self.mlp_grad.data_ptr(),
-                                       L.ptr(self.emb_grad), ws.data_ptr(), L.stream()))
+        L.check(lib.hrf_field_backward_mlp(C.byref(nat.field), C.byref(samples), d_sigma.data_ptr(), d_rgb.data_ptr(),
+                                           feat.data_ptr(), self.mlp_grad.data_ptr(), L.ptr(self.emb_grad), ws.data_ptr(),
+                                           L.stream()))
+        egrid = feat.data_ptr() + 64 * n
+        works = None
+        if self.world == 1 or not self.overlap_allreduce:
+            L.check(lib.hrf_field_backward_tables(C.byref(nat.field), C.byref(samples), self.sg_dev.data_ptr(), egrid,
+                                                  ws.data_ptr(), 0, 4, L.stream()))
+            if self.world > 1:
+                allreduce_bucket_(self.grad, self.pg)
+            launches += 8 + 12 + (1 if self.world > 1 else 0)
+        else:
+            # data parallel: table k's gradient region is reduced (NCCL, its own stream) while table k+1 is still being
+            # scattered; the sum's mean over ranks is folded into Adam's grad_scale
+            works = []
+            for k in range(4):
+                L.check(lib.hrf_field_backward_tables(C.byref(nat.field), C.byref(samples), self.sg_dev.data_ptr(), egrid,
+                                                      ws.data_ptr(), k, 1, L.stream()))
+                works.append(allreduce_bucket_(self.grad[self.regions[k][0]:self.regions[k][1]], self.pg, async_op=True))
+            works.append(allreduce_bucket_(self.grad[self.regions[4][0]:self.regions[4][1]], self.pg, async_op=True))
+            launches += 8 + 15 + 5
         if bwd_events is not None:
             bwd_events[1].record()
-        launches += 8 + 12
         mark("backward")
-        # ---- data parallel: one all-reduce of the flat bucket (sum), mean over ranks folded into Adam's grad_scale
-        if self.world > 1:
-            allreduce_bucket_(self.grad, self.pg)
-            launches += 1
-        self.apply_adam(1.0 / self.world)
+        self.apply_adam(1.0 / self.world, works)
         launches += len(self.params) + 3
         mark("allreduce+adam")
         self.last = {"samples": n, "loss": loss.detach()}
@@ -162,25 +188,26 @@ class FusedTrainer:
             return float(loss.item())
         return launches
 
-    def apply_adam(self, grad_scale: float) -> None:
-        lib, nat = L.lib(), self.nat
+    def apply_adam(self, grad_scale: float, works=None) -> None:
+        """Adam over the bucket in region order; `works` = the 5 pending all-reduces (one per region), each waited for
+        just before the first parameter of its region is updated."""
+        nat = self.nat
         self.t += 1
         lr = self.current_lr()
-        i = 0
+        S = self.model.num_segments
         with torch.no_grad():
-            for s, fg in enumerate(self.model.feature_grids):
-                for k in range(4):
-                    self._adam(i, nat.shadows[s][k], lr, grad_scale)
-                    i += 1
-                self._adam(i, None, lr, grad_scale)
-                i += 1
-            for j in range(i, len(self.params)):          # sigma net, colour net, [camera embeddings]
-                self._adam(j, None, lr, grad_scale)
+            for j, i in enumerate(self.adam_order):
+                region = min(j // S, 4)
+                if works is not None and works[region] is not None:
+                    works[region].wait()
+                    works[region] = None
+                shadow = nat.shadows[i // 5][i % 5] if (i < 5 * S and i % 5 < 4) else None
+                self._adam(i, shadow, lr, grad_scale)
             nat.repack_mlp()
 
     def _adam(self, i: int, shadow: Optional[torch.Tensor], lr: float, grad_scale: float) -> None:
         p = self.params[i]
-        a, b = self.offsets[i], self.offsets[i + 1]
+        a, b = self.slices[i]
         L.check(L.lib().hrf_adam_step(p.data_ptr(), self.exp_avg[a:b].data_ptr(), self.exp_avg_sq[a:b].data_ptr(),
                                       self.grad[a:b].data_ptr(), L.ptr(shadow), b - a, lr, self.betas[0], self.betas[1],
                                       self.eps, self.t, grad_scale, L.stream()))

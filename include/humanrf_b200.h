@@ -206,6 +206,13 @@ int hrf_field_backward(const hrf_field* f, const hrf_samples* s, const hrf_segme
                        float* d_mlp /* fp32 [3072 + 64*color_in_width + 5120]: sigma W1,W2, colour W1,W2,W3 row-major [out,in] */,
                        float* d_camera_embeddings /* fp32 [num_cameras, dim] accumulated into, or NULL */,
                        void* workspace /* 160 bytes per sample (16-byte aligned): d(features) level-major, positions, segment ids */, void* stream);
+/* The same backward in two phases, so that a data-parallel trainer can start reducing one table's gradient while the
+ * next table's scatter still runs: hrf_field_backward == hrf_field_backward_mlp + hrf_field_backward_tables(0, 4).
+ * Table k's gradient is complete after the launch covering grid k; the vector gradients after the last launch. */
+int hrf_field_backward_mlp(const hrf_field* f, const hrf_samples* s, const float* d_sigma, const float* d_rgb,
+                           const void* feat_bf16, float* d_mlp, float* d_camera_embeddings, void* workspace, void* stream);
+int hrf_field_backward_tables(const hrf_field* f, const hrf_samples* s, const hrf_segment_grads* seg_grads,
+                              const void* grid_feat_bf16, const void* workspace, int grid_first, int grid_count, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * tensor_composition_native parity (tensor_composition.cu:120-219): stand-alone fwd/bwd of

@@ -20,7 +20,23 @@ def _subset(b, lo, hi):
                 ri=b["ri"][sel] - lo)
 
 
-def _train(rank, world, port, spans, q):
+def _collect(q, procs, count, timeout=240):
+    """`count` results from the queue, failing at once if a child died instead of waiting out the timeout."""
+    import queue
+    import time
+
+    out, t0 = [], time.time()
+    while len(out) < count:
+        try:
+            out.append(q.get(timeout=2))
+        except queue.Empty:
+            dead = [p.exitcode for p in procs if p.exitcode not in (None, 0)]
+            assert not dead, f"a rank exited with {dead}"
+            assert time.time() - t0 < timeout, "timed out waiting for the ranks"
+    return out
+
+
+def _train(rank, world, port, spans, q, overlap=True):
     import torch.distributed as dist
 
     from humanrf_b200.training import FusedTrainer
@@ -36,35 +52,51 @@ def _train(rank, world, port, spans, q):
     bg_all = torch.rand(512, 3, generator=torch.Generator().manual_seed(9))
     lo, hi = spans[rank]
     sb = {k: v.to(dev).contiguous() for k, v in _subset(b, lo, hi).items()}
-    tr = FusedTrainer(model, lr=1e-2, prune=False, world_size=world)
+    tr = FusedTrainer(model, lr=1e-2, prune=False, world_size=world, overlap_allreduce=overlap)
     for _ in range(STEPS):
         tr.step(sb["o"], sb["d"], sb["frames"], sb["t"], sb["ri"], sb["rgba"], hi - lo, background=bg_all[lo:hi].to(dev))
     torch.cuda.synchronize()
-    if rank == 0:
-        q.put([p.detach().cpu().numpy() for p in model.hot_parameters()])
+    q.put((rank, [p.detach().cpu().numpy() for p in model.hot_parameters()]))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def test_two_rank_dp_equals_single_process(cuda):
+@pytest.mark.parametrize("overlap", [False, True])
+def test_two_rank_dp_equals_single_process(cuda, overlap):
+    """overlap=False: one all-reduce of the whole bucket after the backward; overlap=True: per-table all-reduces that
+    run beside the next table's scatter (FusedTrainer's default)."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
+    init = [p.detach().cpu().numpy() for p in make_model((6,), table_std=0.5, device=cuda)[0].hot_parameters()]
     p = ctx.Process(target=_train, args=(0, 1, 0, [(0, 512)], q))
-    p.start(); ref = q.get(timeout=300); p.join()
-    port = 29600 + os.getpid() % 1000
-    procs = [ctx.Process(target=_train, args=(r, 2, port, [(0, 200), (200, 512)], q)) for r in range(2)]   # unequal shares
+    p.start(); (_, ref), = _collect(q, [p], 1); p.join(timeout=60)
+    port = 29600 + os.getpid() % 1000 + (1 if overlap else 0)
+    procs = [ctx.Process(target=_train, args=(r, 2, port, [(0, 200), (200, 512)], q, overlap)) for r in range(2)]   # unequal shares
     for p in procs:
         p.start()
-    got = q.get(timeout=300)
+    got = dict(_collect(q, procs, 2))
     for p in procs:
-        p.join(timeout=300)
+        p.join(timeout=60)
         assert p.exitcode == 0
-    for a, b in zip(got, ref):
-        moved = np.abs(b).max()
-        assert np.abs(a - b).max() <= 2e-3 * moved + 1e-6, (np.abs(a - b).max(), moved)
+    # the replicas apply the same reduced gradient: they must stay bit-identical
+    diverged = [(i, float(np.abs(a - b).max())) for i, (a, b) in enumerate(zip(got[0], got[1])) if not np.array_equal(a, b)]
+    print("replica divergence:", diverged)
+    # Against single-process training on the union batch.  Adam (eps = 1e-15) moves an entry by ~lr whatever the size of
+    # its gradient, so an entry whose contributions cancel to rounding noise may step the other way: compare the bulk
+    # (relative L2 of the difference against the distance trained) and bound the share of such outliers.
+    bad = []
+    for i, (a, b, p0) in enumerate(zip(got[0], ref, init)):
+        diff, moved = np.abs(a - b), np.linalg.norm(b - p0)
+        rel = np.linalg.norm(a - b) / max(moved, 1e-12)
+        outliers = float((diff > 2e-3).mean())
+        print(f"param {i}: size {a.size} max diff {diff.max():.3e} rel L2 {rel:.3e} outliers {outliers:.2e}")
+        if not (rel <= 2e-2 and outliers <= 1e-3):
+            bad.append((i, rel, outliers, diff.max()))
+    assert not diverged, diverged
+    assert not bad, bad
 
 
 def test_tile_sharded_render_equals_monolithic(cuda):

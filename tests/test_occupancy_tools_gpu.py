@@ -53,7 +53,9 @@ def test_carve_vs_reference_extension(cuda):
     args = (torch.from_numpy(sc["masks"]).to(cuda), torch.from_numpy(sc["projection_matrices"]).to(cuda),
             torch.from_numpy(sc["landscape"]).to(cuda), thr, G, 512, 384)
     want = ref.generate_from_masks(*args)
-    got = _carve(sc, thr, G, cuda)
+    from humanrf_b200.toolbox import occupancy_grid_generation_native as ours
+
+    got = ours.generate_from_masks(*args)
     torch.cuda.synchronize()
     diff = int((want != got).sum())
     occ = int((want == 255).sum())
@@ -66,7 +68,7 @@ def test_carve_vs_reference_extension(cuda):
         return e0.elapsed_time(e1) / 5
 
     print(f"carve vs reference: {diff} of {G ** 3} voxels differ, {occ} occupied; "
-          f"ours {ms(lambda: _carve(sc, thr, G, cuda)):.3f} ms, reference {ms(lambda: ref.generate_from_masks(*args)):.3f} ms")
+          f"ours {ms(lambda: ours.generate_from_masks(*args)):.3f} ms, reference {ms(lambda: ref.generate_from_masks(*args)):.3f} ms")
     assert 0 < occ < G ** 3 and diff <= 2e-5 * G ** 3
 
 
