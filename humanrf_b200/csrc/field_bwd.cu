@@ -129,7 +129,7 @@ __device__ __forceinline__ void red_add2(float* addr, float a, float b) {
 
 // Table / vector gradient scatter (tcnn kernel_grid_backward + compose_tensors_backward,
 // tensor_composition.cu:57-118) as a separate high-occupancy kernel.
-//   thread = (chunk of kChunk consecutive samples, level, grid): blockIdx.y = level*4 + grid.
+//   thread = (chunk of kChunk consecutive samples, level, grid): blockIdx.y = level * grid_count + (grid - grid_first).
 // Consecutive samples of a ray are 4e-4 apart, so at most levels they stay in the same grid cell for several
 // samples: the thread keeps the cell's 8 corner indices / values in registers, accumulates w*g per corner while
 // the cell does not change and issues the 8 vector REDs once per RUN of samples (not once per sample).  The
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(256, 3) grid_scatter_kernel(const __grid_const
       accy[q] = __fmaf_rn(w[q], gy, accy[q]);
     }
     if (a.egrid != nullptr) {  // interpolated grid features saved by the forward
-      const uint32_t ev = __ldg(a.egrid + (size_t)blockIdx.y * n + i);
+      const uint32_t ev = __ldg(a.egrid + (size_t)(4 * l + k) * n + i);
       ex = bf16_lo(ev), ey = bf16_hi(ev);
     } else {
 #pragma unroll

@@ -2,6 +2,8 @@
 //   * visual-hull occupancy carving  (actorshq/toolbox/native/occupancy_grid_generation.cu:16-81)
 //   * union + population count of occupancy grids for adaptive temporal partitioning
 //     (humanrf/adaptive_temporal_partitioning.py:11-26, equations (2)-(4))
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace hrf {
@@ -39,7 +41,7 @@ __global__ void __launch_bounds__(256) carve_kernel(const __grid_constant__ Carv
   __syncthreads();
   const uint32_t G = (uint32_t)a.G, n = G * G * G;   // G <= 1024 (host check): 32-bit index arithmetic
   const uint8_t* __restrict__ masks = a.masks;
-  // persistent CTAs: the staging above is paid once per CTA, not once per 256 voxels
+  // grid-stride: the staging above is paid once per CTA, not once per 256 voxels
   for (uint32_t v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
   const uint32_t gx = v % G, gyz = v / G, gy = gyz % G, gz = gyz / G;
   const float inv = (float)(G - 1);
@@ -100,8 +102,12 @@ extern "C" int hrf_occupancy_from_masks(const uint8_t* masks, const float* proje
   CarveArgs a{masks, projection_matrices, landscape_modes, camera_coverage_threshold, num_cameras, grid_resolution, width,
               height, occupancy_grid};
   const int64_t n = (int64_t)grid_resolution * grid_resolution * grid_resolution;
-  const int64_t want = (n + 255) / 256, cap = (int64_t)sm_count() * 8;
-  carve_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
+  // 16 strided chunks of 256 voxels per CTA: the matrix staging is amortised 16x while the grid stays many waves deep
+  // (voxels differ a lot in cost -- early exits -- so a one-wave persistent grid leaves SMs idle at the tail)
+  const int64_t want = (n + 255) / 256, floor_ = (int64_t)sm_count() * 8;
+  static const int chunks = [] { const char* e = getenv("HRF_CARVE_CHUNKS"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 16; }();
+  const int64_t blocks = want <= floor_ ? want : (want / chunks > floor_ ? want / chunks : floor_);
+  carve_kernel<<<(unsigned)blocks, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(a);
   HRF_CHECK_LAUNCH();
   return 0;
 }

@@ -324,8 +324,9 @@ class _NativeField:
                                                  L.stream()))
         return sigma
 
-    def backward(self, samples: L.Samples, d_sigma, d_rgb, feat, grad_tensors: List[torch.Tensor]):
-        """grad_tensors: fp32 buffers in hot_parameters() order (accumulated into)."""
+    def backward(self, samples: L.Samples, d_sigma, d_rgb, feat, grad_tensors: List[torch.Tensor], per_table: bool = False):
+        """grad_tensors: fp32 buffers in hot_parameters() order (accumulated into).  per_table launches the scatter once
+        per grid (the schedule the data-parallel trainer overlaps with its all-reduces) instead of once for all four."""
         m = self.model
         dev = self._device()
         sg = (L.SegmentGrads * m.num_segments)()
@@ -342,9 +343,16 @@ class _NativeField:
         ws = torch.empty(int(samples.num_samples) * 40, dtype=torch.float32, device=dev)   # 160 B / sample
         n = int(samples.num_samples)
         egrid = feat.data_ptr() + 64 * n if (feat is not None and feat.numel() >= n * 160 and n > 0) else None
-        L.check(L.lib().hrf_field_backward(C.byref(self.field), C.byref(samples), sg_dev.data_ptr(), L.ptr(d_sigma),
-                                           L.ptr(d_rgb), L.ptr(feat), egrid, d_mlp.data_ptr(), L.ptr(d_emb),
-                                           ws.data_ptr(), L.stream()))
+        if per_table:
+            L.check(L.lib().hrf_field_backward_mlp(C.byref(self.field), C.byref(samples), L.ptr(d_sigma), L.ptr(d_rgb),
+                                                   L.ptr(feat), d_mlp.data_ptr(), L.ptr(d_emb), ws.data_ptr(), L.stream()))
+            for k in range(4):
+                L.check(L.lib().hrf_field_backward_tables(C.byref(self.field), C.byref(samples), sg_dev.data_ptr(), egrid,
+                                                          ws.data_ptr(), k, 1, L.stream()))
+        else:
+            L.check(L.lib().hrf_field_backward(C.byref(self.field), C.byref(samples), sg_dev.data_ptr(), L.ptr(d_sigma),
+                                               L.ptr(d_rgb), L.ptr(feat), egrid, d_mlp.data_ptr(), L.ptr(d_emb),
+                                               ws.data_ptr(), L.stream()))
         grad_tensors[i].add_(d_mlp[:MLP_SIGMA_PARAMS])
         grad_tensors[i + 1].add_(d_mlp[MLP_SIGMA_PARAMS:])
         return sg_dev  # keep alive until the kernel has run (stream-ordered free is safe, but be explicit)

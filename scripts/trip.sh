@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-for f in tests/test_dp_gpu.py tests/test_occupancy_tools_gpu.py; do
-  timeout 500 python -m pytest $f -q -m gpu -s --no-header -p no:cacheprovider > gpurun_out/$(basename $f .py).log 2>&1; echo "$f exit=$?"; tail -2 gpurun_out/$(basename $f .py).log
-done
-grep -h "carve vs\|^param\|replicas" gpurun_out/*.log
+timeout 200 python -m pytest tests/test_dp_gpu.py -q -m gpu -s --no-header -p no:cacheprovider -k two_rank > gpurun_out/test_dp_gpu.log 2>&1; echo "dp exit=$?"
+grep -h "^param\|replica\|passed\|failed\|Error" gpurun_out/test_dp_gpu.log | head -30
+timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --mode train --steps 20 --warmup 5 > gpurun_out/bench_train_2gpu.json 2> gpurun_out/bench_train_2gpu.err; grep -o '"value": [0-9.]*\|"ms_per_step": [0-9.]*' gpurun_out/bench_train_2gpu.json | head -3
+timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 20 --warmup 5 > gpurun_out/bench_render_2gpu.json 2> gpurun_out/bench_render_2gpu.err; grep -o '"value": [0-9.]*\|"ms_per_step": [0-9.]*' gpurun_out/bench_render_2gpu.json | head -3

@@ -68,6 +68,31 @@ def test_field_backward_matches_autograd(cuda, segs, use_saved_features):
     assert es < 3e-2 and ec < 3e-2
 
 
+@pytest.mark.parametrize("use_saved_features", [True, False])
+def test_per_table_backward_equals_single_launch(cuda, use_saved_features):
+    """hrf_field_backward == hrf_field_backward_mlp + 4 x hrf_field_backward_tables(k, 1): the schedule the
+    data-parallel trainer overlaps with its per-table all-reduces (differences: fp32 atomic ordering only)."""
+    _, m, frames = make_pair((6, 6))
+    b = synthetic_rays(300, 40, frames, ragged=True, seed=3)
+    pos, dirs, fr = positions_of(b), b["d"][b["ri"]], b["frames"][b["ri"]]
+    n = pos.shape[0]
+    g = torch.Generator().manual_seed(7)
+    d_sigma, d_rgb = (torch.randn(n, generator=g) * 1e-2).to(cuda), torch.randn(n, 3, generator=g).to(cuda)
+    nat = m.native()
+    s = nat.samples_query(pos.to(cuda).contiguous(), dirs.to(cuda).contiguous(), fr.to(cuda).contiguous())
+    _, _, _, feat = nat.forward(s, 1, want_geo=False, want_feat=True)
+    out = []
+    for per_table in (False, True):
+        grads = [torch.zeros_like(p) for p in m.hot_parameters()]
+        nat.backward(s, d_sigma, d_rgb, feat if use_saved_features else None, grads, per_table=per_table)
+        torch.cuda.synchronize()
+        out.append(grads)
+    for i, (a, b_) in enumerate(zip(*out)):
+        assert a.abs().sum() > 0
+        e = _relnorm(b_, a)
+        assert e < 1e-5, (i, e)
+
+
 def test_render_autograd_end_to_end(cuda):
     """prune_samples + render + reference loss (trainer.py:205-255) through the module API vs the oracle."""
     from humanrf_b200.volume_rendering import prune_samples, render

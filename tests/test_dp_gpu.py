@@ -93,7 +93,7 @@ def test_two_rank_dp_equals_single_process(cuda, overlap):
         rel = np.linalg.norm(a - b) / max(moved, 1e-12)
         outliers = float((diff > 2e-3).mean())
         print(f"param {i}: size {a.size} max diff {diff.max():.3e} rel L2 {rel:.3e} outliers {outliers:.2e}")
-        if not (rel <= 2e-2 and outliers <= 1e-3):
+        if not (rel <= 1e-4 and outliers <= 1e-5):      # measured: rel 2e-7 .. 2e-6, no outliers
             bad.append((i, rel, outliers, diff.max()))
     assert not diverged, diverged
     assert not bad, bad
