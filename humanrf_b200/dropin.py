@@ -19,6 +19,8 @@ _MAP = {
     "actorshq.dataset.input_batch": "humanrf_b200.dataset.input_batch",
     "actorshq.dataset.ray_sampler_native": "humanrf_b200.dataset.ray_sampler_native",
     "actorshq.dataset.occupancy_grid_native": "humanrf_b200.dataset.occupancy_grid_native",
+    "actorshq.toolbox.occupancy_grid_generation_native": "humanrf_b200.toolbox.occupancy_grid_generation_native",
+    "humanrf.adaptive_temporal_partitioning": "humanrf_b200.adaptive_temporal_partitioning",
 }
 
 
