@@ -30,6 +30,25 @@ def deal_round_robin(items: Sequence, rank: int, world: int) -> List:
     return [x for i, x in enumerate(items) if i % world == rank]
 
 
+def grid_major_bucket_layout(sizes: Sequence[int], num_segments: int):
+    """Layout of the flat gradient bucket for parameters given in hot_parameters() order (per segment: grid 0..3,
+    vectors; then the MLPs and, if any, the camera embeddings).  Returns (slices, regions, order):
+    slices[i] = (start, end) of parameter i inside the bucket; regions = 5 contiguous (start, end) spans -- grid k of
+    every segment for k = 0..3, then everything else; order = parameter indices in bucket order.  Region k is complete
+    once the scatter launch of grid k has run, which is what lets its all-reduce overlap the next launch."""
+    S = num_segments
+    order = [5 * s + k for k in range(4) for s in range(S)] + [5 * s + 4 for s in range(S)] + list(range(5 * S, len(sizes)))
+    slices: List = [None] * len(sizes)
+    starts, pos = [], 0
+    for j, i in enumerate(order):
+        if j % S == 0 and j <= 4 * S:
+            starts.append(pos)
+        slices[i] = (pos, pos + int(sizes[i]))
+        pos = slices[i][1]
+    regions = list(zip(starts, starts[1:] + [pos]))
+    return slices, regions, order
+
+
 def union_batch_loss_scale(num_rays_local: int, device, group=None):
     """world * R_local / R_total, so that summing rank gradients and dividing by world gives the gradient of the
     mean loss over the union of all ranks' rays.  One 8-byte all-reduce; the result stays ON THE DEVICE (a 0-dim

@@ -21,7 +21,7 @@ import numpy as np
 import torch
 
 from . import _lib as L
-from .parallel import allreduce_bucket_, union_batch_loss_scale
+from .parallel import allreduce_bucket_, grid_major_bucket_layout, union_batch_loss_scale
 from .scene_representation.humanrf import HumanRF
 from .volume_rendering import ray_offsets
 
@@ -43,19 +43,8 @@ class FusedTrainer:
         # Bucket layout, GRID-MAJOR: [grid 0 of every segment | grid 1 ... | grid 2 ... | grid 3 ... | vectors of every
         # segment, MLPs, camera embeddings].  Region k is complete as soon as the scatter launch of grid k has run, so under
         # data parallelism its all-reduce overlaps the scatter of grid k+1 (hot_parameters() itself is segment-major).
-        order = [5 * s_ + k for k in range(4) for s_ in range(S)] + [5 * s_ + 4 for s_ in range(S)] + \
-            list(range(5 * S, len(self.params)))
-        self.slices = [None] * len(self.params)
-        pos = 0
-        self.regions = []
-        for j, i in enumerate(order):
-            if j % S == 0 and j <= 4 * S:
-                self.regions.append(pos)
-            self.slices[i] = (pos, pos + self.params[i].numel())
-            pos = self.slices[i][1]
-        total = pos
-        self.regions = [(a, b) for a, b in zip(self.regions, self.regions[1:] + [total])]     # 4 table regions + the tail
-        self.adam_order = order
+        self.slices, self.regions, self.adam_order = grid_major_bucket_layout([p.numel() for p in self.params], S)
+        total = self.regions[-1][1]
         self.grad = torch.zeros(total, dtype=torch.float32, device=dev)       # the all-reduce bucket
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)

@@ -7,8 +7,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from humanrf_b200.parallel import (allreduce_bucket_, broadcast_parameters_, deal_round_robin, shard_range,
-                                   union_batch_loss_scale)
+from humanrf_b200.parallel import (allreduce_bucket_, broadcast_parameters_, deal_round_robin, grid_major_bucket_layout,
+                                   shard_range, union_batch_loss_scale)
 
 
 def test_shard_range_and_round_robin_cover_everything():
@@ -21,6 +21,33 @@ def test_shard_range_and_round_robin_cover_everything():
     seq = [(c, f) for c in range(5) for f in range(7)]
     dealt = [deal_round_robin(seq, r, 4) for r in range(4)]
     assert sorted(sum(dealt, [])) == sorted(seq)
+
+
+def test_grid_major_bucket_layout():
+    for S, extra in ((1, 2), (2, 2), (3, 3), (5, 2)):
+        sizes = []
+        for s in range(S):
+            sizes += [1000 + 10 * s + k for k in range(4)] + [77 + s]           # 4 grids + vectors per segment
+        sizes += [3072, 7168, 320][:extra]                                      # sigma net, colour net, [embeddings]
+        slices, regions, order = grid_major_bucket_layout(sizes, S)
+        assert sorted(order) == list(range(len(sizes))) and len(regions) == 5
+        # the slices tile the bucket exactly, in `order`
+        pos = 0
+        for i in order:
+            assert slices[i] == (pos, pos + sizes[i])
+            pos = slices[i][1]
+        assert regions[0][0] == 0 and regions[-1][1] == pos and all(a[1] == b[0] for a, b in zip(regions, regions[1:]))
+        for k in range(4):                                                      # region k = grid k of every segment, nothing else
+            inside = [i for i in range(len(sizes)) if regions[k][0] <= slices[i][0] and slices[i][1] <= regions[k][1]]
+            assert inside == [5 * s + k for s in range(S)]
+        # sigma net and colour net stay adjacent (the fused backward writes them as one block)
+        assert slices[5 * S][1] == slices[5 * S + 1][0]
+
+
+def test_allreduce_helpers_are_no_ops_without_a_process_group():
+    t = torch.arange(4.0)
+    assert allreduce_bucket_(t) is t and allreduce_bucket_(t, async_op=True) is None
+    assert union_batch_loss_scale(7, "cpu") == 1.0
 
 
 def _worker(rank, world, port, ray_counts, out):
@@ -36,7 +63,12 @@ def _worker(rank, world, port, ray_counts, out):
     loss = torch.nn.functional.huber_loss(xs @ w, ys, delta=0.01, reduction="mean")   # per-rank mean, as FusedTrainer
     (loss * union_batch_loss_scale(ray_counts[rank], "cpu")).backward()
     bucket = w.grad.clone()
+    regions = w.grad.clone()                                     # the same bucket reduced region by region, asynchronously
     allreduce_bucket_(bucket)
+    works = [allreduce_bucket_(regions[a:b], async_op=True) for a, b in ((0, 5), (5, 6), (6, 16))]
+    for wk in works:
+        wk.wait()
+    assert torch.equal(regions, bucket)                          # FusedTrainer's overlapped schedule == one message
     bucket /= world                                              # Adam's grad_scale = 1/world
     p = torch.full((4,), float(rank))
     broadcast_parameters_([p], src=0)
