@@ -262,7 +262,9 @@ __device__ __forceinline__ void write_color_input(const hrf_field& f, unsigned c
 // If `egrid` is not NULL the per-grid interpolated features e_k (before composition) are also stored, bf16x2, as
 // egrid[(level*4 + grid) * n + i]: the backward scatter needs them for the vector gradients and then does not have
 // to gather the tables a second time.
-template <bool kSaveGrid = false>
+// kLevelUnroll = 4 keeps four levels' gathers in flight per thread; 2 / 1 shrink the unrolled code.  The forward kernel
+// runs fastest with 1 (it was instruction-cache bound at 4: 117 KB of SASS), see launch_field_forward.
+template <bool kSaveGrid = false, int kLevelUnroll = 4>
 __device__ __forceinline__ void encode_to_smem(const hrf_field& f, const Sample& s, unsigned char* abuf, int row,
                                                uint32_t* egrid = nullptr, int64_t i = 0, int64_t n = 0) {
   const uint32_t roff = a_row_off(row);
@@ -280,39 +282,44 @@ __device__ __forceinline__ void encode_to_smem(const hrf_field& f, const Sample&
   const uint32_t hmask = sg->hashed_mask;
   const VecTap tx = make_tap(s.x, f.vec_res, 0), ty = make_tap(s.y, f.vec_res, 1), tz = make_tap(s.z, f.vec_res, 2),
                tt = make_tap(s.t, f.vec_res, 3);
-#pragma unroll 1
-  for (int kg = 0; kg < 4; ++kg) {
-    uint32_t pk[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int l = kg * 4 + j;
-      const float scale = f.level_scale[l];
-      const uint32_t res = f.level_res[l];
-      const uint32_t off = sg->level_offset[l];
-      const uint32_t size = sg->level_size[l];
-      const bool hashed = (hmask >> l) & 1u;
-      const Cell cx = to_cell(scale, s.x), cy = to_cell(scale, s.y), cz = to_cell(scale, s.z),
-                 ct = to_cell(scale, s.t);
-      // decomposition4d.py:126-129 : xyz, xyt, yzt, xzt
-      const float2 e0 = gather_level(g0 + off, hashed, res, size, cx, cy, cz);
-      const float2 e1 = gather_level(g1 + off, hashed, res, size, cx, cy, ct);
-      const float2 e2 = gather_level(g2 + off, hashed, res, size, cy, cz, ct);
-      const float2 e3 = gather_level(g3 + off, hashed, res, size, cx, cz, ct);
-      const float2 vx = lerp_tap(vec, tx, 2 * l), vy = lerp_tap(vec, ty, 2 * l), vz = lerp_tap(vec, tz, 2 * l),
-                   vt = lerp_tap(vec, tt, 2 * l);
-      // tensor_composition.cu:49-52 : xyz*v_t + xyt*v_z + yzt*v_x + xzt*v_y
-      const float o0 = e0.x * vt.x + e1.x * vz.x + e2.x * vx.x + e3.x * vy.x;
-      const float o1 = e0.y * vt.y + e1.y * vz.y + e2.y * vx.y + e3.y * vy.y;
-      pk[j] = pack_bf16x2(o0, o1);
-      if (kSaveGrid && egrid != nullptr) {
-        uint32_t* eg = egrid + (size_t)(4 * l) * n + i;
-        eg[0] = pack_bf16x2(e0.x, e0.y);
-        eg[n] = pack_bf16x2(e1.x, e1.y);
-        eg[2 * n] = pack_bf16x2(e2.x, e2.y);
-        eg[3 * n] = pack_bf16x2(e3.x, e3.y);
-      }
+  auto one_level = [&](int l) -> uint32_t {
+    const float scale = f.level_scale[l];
+    const uint32_t res = f.level_res[l];
+    const uint32_t off = sg->level_offset[l];
+    const uint32_t size = sg->level_size[l];
+    const bool hashed = (hmask >> l) & 1u;
+    const Cell cx = to_cell(scale, s.x), cy = to_cell(scale, s.y), cz = to_cell(scale, s.z), ct = to_cell(scale, s.t);
+    // decomposition4d.py:126-129 : xyz, xyt, yzt, xzt
+    const float2 e0 = gather_level(g0 + off, hashed, res, size, cx, cy, cz);
+    const float2 e1 = gather_level(g1 + off, hashed, res, size, cx, cy, ct);
+    const float2 e2 = gather_level(g2 + off, hashed, res, size, cy, cz, ct);
+    const float2 e3 = gather_level(g3 + off, hashed, res, size, cx, cz, ct);
+    const float2 vx = lerp_tap(vec, tx, 2 * l), vy = lerp_tap(vec, ty, 2 * l), vz = lerp_tap(vec, tz, 2 * l),
+                 vt = lerp_tap(vec, tt, 2 * l);
+    // tensor_composition.cu:49-52 : xyz*v_t + xyt*v_z + yzt*v_x + xzt*v_y
+    const float o0 = e0.x * vt.x + e1.x * vz.x + e2.x * vx.x + e3.x * vy.x;
+    const float o1 = e0.y * vt.y + e1.y * vz.y + e2.y * vx.y + e3.y * vy.y;
+    if (kSaveGrid && egrid != nullptr) {
+      uint32_t* eg = egrid + (size_t)(4 * l) * n + i;
+      eg[0] = pack_bf16x2(e0.x, e0.y);
+      eg[n] = pack_bf16x2(e1.x, e1.y);
+      eg[2 * n] = pack_bf16x2(e2.x, e2.y);
+      eg[3 * n] = pack_bf16x2(e3.x, e3.y);
     }
-    *reinterpret_cast<uint4*>(abuf + kg * kAChunk + roff) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    return pack_bf16x2(o0, o1);
+  };
+  if constexpr (kLevelUnroll == 4) {
+#pragma unroll 1
+    for (int kg = 0; kg < 4; ++kg) {
+      uint32_t pk[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) pk[j] = one_level(kg * 4 + j);
+      *reinterpret_cast<uint4*>(abuf + kg * kAChunk + roff) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    }
+  } else {
+#pragma unroll kLevelUnroll
+    for (int l = 0; l < HRF_N_LEVELS; ++l)
+      *reinterpret_cast<uint32_t*>(abuf + (l >> 2) * kAChunk + roff + (l & 3) * 4) = one_level(l);
   }
 }
 

@@ -101,7 +101,7 @@ __device__ __forceinline__ void store_hidden(unsigned char* hbuf, int row, const
   }
 }
 
-template <bool kSimt, int kCtasPerSm, bool kSaveGrid = false>
+template <bool kSimt, int kCtasPerSm, bool kSaveGrid = false, int kLevelUnroll = 4>
 __global__ void __launch_bounds__(kTile, kCtasPerSm) field_forward_kernel(const __grid_constant__ FieldArgs args) {
   extern __shared__ unsigned char smem_raw[];
   FwdSmem& sm = *reinterpret_cast<FwdSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(kTile, kCtasPerSm) field_forward_kernel(const 
       }
     }
     const Sample s = load_sample(f, args.s, valid ? i : n);
-    encode_to_smem<kSaveGrid>(f, s, sm.a, tid, (kSaveGrid && valid && s.seg != nullptr) ? args.egrid : nullptr, i, n);
+    encode_to_smem<kSaveGrid, kLevelUnroll>(f, s, sm.a, tid, (kSaveGrid && valid && s.seg != nullptr) ? args.egrid : nullptr, i, n);
     if (args.feat != nullptr && valid) {
       const uint32_t ro = a_row_off(tid);
 #pragma unroll
@@ -249,8 +249,8 @@ using namespace hrf;
 static int launch_field_forward(const FieldArgs& a, int mlp_impl, cudaStream_t st, bool persistent_full) {
   const int64_t tiles = (a.s.num_samples + kTile - 1) / kTile;
   const int smem = (int)(offsetof(FwdSmem, w) + w_blob_bytes(a.f.color_in_width)) + 128;
-  // CTAs per SM, measured on B200 on the bench batch: 4 (118 regs) 1.291 ms, 5 (96 regs) 1.265 ms, 6 (80 regs,
-  // spills, less gather ILP per thread) 1.475 ms.  HRF_FWD_CTAS overrides for experiments.
+  // CTAs per SM, measured on B200 on the bench batch with 4 levels unrolled: 4 (118 regs) 1.291 ms, 5 (96 regs)
+  // 1.265 ms, 6 (80 regs, spills) 1.475 ms.  HRF_FWD_CTAS overrides for experiments (4 and 6 keep the 4-level unroll).
   static const int ctas_per_sm = [] {
     const char* e = getenv("HRF_FWD_CTAS");
     const int v = e ? atoi(e) : 5;
@@ -266,9 +266,18 @@ static int launch_field_forward(const FieldArgs& a, int mlp_impl, cudaStream_t s
     kernel<<<grid, kTile, smem, st>>>(a);
     return 0;
   };
+  // Levels unrolled in the encode loop (HRF_FWD_UNROLL = 1 | 2 | 4).  Measured on B200 on the bench batch
+  // (profiles/r1_fwd_unroll.txt): 4 levels -> 1.283 ms (7 344 SASS instructions = 117 KB, ncu: no-instruction stalls
+  // 2.3 per issue), 2 -> 1.145 ms, 1 -> 1.034 ms (3 336 instructions): the instruction cache, not gather ILP, was
+  // the limiter.  Default 1.
+  static const int unroll = [] { const char* e = getenv("HRF_FWD_UNROLL"); const int v = e ? atoi(e) : 1; return (v == 2 || v == 4) ? v : 1; }();
   int rc;
   if (mlp_impl != 0) rc = launch(field_forward_kernel<true, 4>);
+  else if (a.egrid != nullptr && unroll == 2) rc = launch(field_forward_kernel<false, 5, true, 2>);
+  else if (a.egrid != nullptr && unroll == 1) rc = launch(field_forward_kernel<false, 5, true, 1>);
   else if (a.egrid != nullptr) rc = launch(field_forward_kernel<false, 5, true>);   // training forward: also saves e_k
+  else if (ctas == 5 && unroll == 2) rc = launch(field_forward_kernel<false, 5, false, 2>);
+  else if (ctas == 5 && unroll == 1) rc = launch(field_forward_kernel<false, 5, false, 1>);
   else if (ctas == 6) rc = launch(field_forward_kernel<false, 6>);
   else if (ctas == 4) rc = launch(field_forward_kernel<false, 4>);
   else rc = launch(field_forward_kernel<false, 5>);
