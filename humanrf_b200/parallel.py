@@ -49,6 +49,30 @@ def grid_major_bucket_layout(sizes: Sequence[int], num_segments: int):
     return slices, regions, order
 
 
+def active_segments(frame_to_segment: torch.Tensor, frame_numbers: torch.Tensor, num_segments: int) -> torch.Tensor:
+    """bool [num_segments], on frame_numbers' device: the temporal segments the batch's frames fall into
+    (humanrf.py:162-163).  Only these take part in a training step: the reference never calls the other segments'
+    encodings, their .grad stays None (trainer.py:174 zero_grad(set_to_none=True)) and torch.optim.Adam leaves their
+    parameters, moments and per-parameter step counters untouched."""
+    lut = frame_to_segment.to(frame_numbers.device)
+    f = frame_numbers.reshape(-1).long()
+    ok = (f >= 0) & (f < lut.numel())
+    seg = torch.where(ok, lut[f.clamp(0, lut.numel() - 1)].long(), torch.full_like(f, -1))
+    used = torch.zeros(num_segments + 1, dtype=torch.bool, device=f.device)
+    used[(seg + 1).clamp(0, num_segments)] = True          # slot 0 collects frames without a segment
+    return used[1:]
+
+
+def mask_inactive_segment_grads(grads: List, active: Sequence[bool]) -> List:
+    """grads in hot_parameters() order (per segment: 4 grids + vectors, then the rest): None for the five tensors of
+    every segment that is not active, as autograd gives the reference for segments it did not call."""
+    out = list(grads)
+    for s, a in enumerate(active):
+        if not a:
+            out[5 * s:5 * s + 5] = [None] * 5
+    return out
+
+
 def union_batch_loss_scale(num_rays_local: int, device, group=None):
     """world * R_local / R_total, so that summing rank gradients and dividing by world gives the gradient of the
     mean loss over the union of all ranks' rays.  One 8-byte all-reduce; the result stays ON THE DEVICE (a 0-dim

@@ -116,16 +116,31 @@ class HumanRF(torch.nn.Module):
 
     # ------------------------------------------------------------------ reference API
     def density(self, query_input: QueryInput) -> QueryOutput:
+        needs_grad = self._needs_grad()
+        active = self.active_segment_list(query_input.frame_numbers, query_input.unique_frame_numbers) if needs_grad else None
         sigma, geo, _ = _FieldFunction.apply(self, 0, query_input.positions, None, query_input.frame_numbers, None,
-                                             self._needs_grad(), *self.hot_parameters())
+                                             needs_grad, active, *self.hot_parameters())
         return QueryOutput(density=sigma, geometry_features=geo)
 
     def forward(self, query_input: QueryInput) -> QueryOutput:
         # humanrf.py:194-204: the camera embedding is looked up while training and is all zeros otherwise
         cams = query_input.camera_numbers if (self.camera_embedding_dim > 0 and query_input.is_training) else None
+        needs_grad = self._needs_grad()
+        active = self.active_segment_list(query_input.frame_numbers, query_input.unique_frame_numbers) if needs_grad else None
         sigma, geo, rgb = _FieldFunction.apply(self, 1, query_input.positions, query_input.directions,
-                                               query_input.frame_numbers, cams, self._needs_grad(), *self.hot_parameters())
+                                               query_input.frame_numbers, cams, needs_grad, active, *self.hot_parameters())
         return QueryOutput(density=sigma, geometry_features=geo, radiance=rgb)
+
+    def active_segment_list(self, frame_numbers, unique_frame_numbers=None) -> Optional[List[bool]]:
+        """Which temporal segments a batch touches (humanrf.py:162-163), as a host list; None for a single-segment
+        model (nothing to decide, no host sync).  The reference only runs -- and so only gives a gradient to -- these
+        segments; `unique_frame_numbers` is the per-ray set the DataLoader provides (data_loader.py:648)."""
+        if self.num_segments == 1:
+            return None
+        from ..parallel import active_segments
+
+        src = unique_frame_numbers if unique_frame_numbers is not None else frame_numbers
+        return active_segments(self.frame_numbers_to_segment_numbers, src, self.num_segments).cpu().tolist()
 
     def _needs_grad(self) -> bool:
         # ctx.needs_input_grad ignores torch.no_grad(); decide outside whether to save the backward buffers
@@ -370,7 +385,8 @@ class _FieldFunction(torch.autograd.Function):
     """autograd wrapper of the fused kernels in QueryInput form (humanrf.py:158-208)."""
 
     @staticmethod
-    def forward(ctx, model: HumanRF, mode: int, positions, directions, frame_numbers, camera_numbers, needs_grad, *params):
+    def forward(ctx, model: HumanRF, mode: int, positions, directions, frame_numbers, camera_numbers, needs_grad, active,
+                *params):
         nat = model.native()
         pos = L.require_cuda(_as_f32c(positions), "positions")
         dirs = None if directions is None else L.require_cuda(_as_f32c(directions), "directions")
@@ -378,7 +394,7 @@ class _FieldFunction(torch.autograd.Function):
         cams = None if camera_numbers is None else L.require_cuda(_as_frames(camera_numbers), "camera_numbers")
         samples = nat.samples_query(pos, dirs, frames, cams)
         sigma, geo, rgb, feat = nat.forward(samples, mode, want_geo=True, want_feat=needs_grad)
-        ctx.model, ctx.mode = model, mode
+        ctx.model, ctx.mode, ctx.active = model, mode, active
         ctx.save_for_backward(pos, dirs if dirs is not None else pos, frames, feat if feat is not None else pos,
                               cams if cams is not None else frames)
         ctx.has_dirs, ctx.has_cams = dirs is not None, cams is not None
@@ -403,4 +419,8 @@ class _FieldFunction(torch.autograd.Function):
             ds = torch.zeros(pos.shape[0], dtype=torch.float32, device=pos.device)
         keep = nat.backward(samples, ds, dr, feat, grads)
         del keep
-        return (None, None, None, None, None, None, None, *grads)
+        if ctx.active is not None:      # segments the batch did not touch get no gradient at all (None), as in the reference
+            from ..parallel import mask_inactive_segment_grads
+
+            grads = mask_inactive_segment_grads(grads, ctx.active)
+        return (None, None, None, None, None, None, None, None, *grads)

@@ -19,9 +19,10 @@ from typing import List, Optional
 
 import numpy as np
 import torch
+import torch.distributed as dist
 
 from . import _lib as L
-from .parallel import allreduce_bucket_, grid_major_bucket_layout, union_batch_loss_scale
+from .parallel import active_segments, allreduce_bucket_, grid_major_bucket_layout, union_batch_loss_scale
 from .scene_representation.humanrf import HumanRF
 from .volume_rendering import ray_offsets
 
@@ -49,7 +50,8 @@ class FusedTrainer:
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
         self.grad_views = [self.grad[a:b] for a, b in self.slices]
-        self.t = 0
+        self.t = 0                                  # optimiser steps taken (drives the learning-rate schedule)
+        self.steps = [0] * len(self.params)         # torch.optim.Adam's per-parameter state['step'] (bias corrections)
         self.gen = torch.Generator(device=dev).manual_seed(seed)
         self.nat = model.native()
         sg = (L.SegmentGrads * S)()
@@ -67,7 +69,9 @@ class FusedTrainer:
 
     # ----------------------------------------------------------------------------------------------
     def current_lr(self) -> float:
-        return self.lr * self.lr_decay ** min(self.t / self.max_steps, 1.0)  # run.py:102-104
+        """LambdaLR of run.py:102-104 evaluated at the number of COMPLETED steps: the scheduler is stepped after the
+        optimiser (trainer.py:251-253), so the first update runs at the full learning rate."""
+        return self.lr * self.lr_decay ** min(self.t / self.max_steps, 1.0)
 
     def step(self, o, d, frames, t, ri, rgba, num_rays: int, kernel_event=None, return_loss: bool = False,
              background: Optional[torch.Tensor] = None, cameras: Optional[torch.Tensor] = None, bwd_events=None):
@@ -86,6 +90,15 @@ class FusedTrainer:
         mark("start")
         step = self.step_size
         t = t.reshape(-1)
+        # Segments this batch touches (humanrf.py:162-179): the reference gives the others no gradient, so Adam leaves
+        # their parameters, moments and step counters alone.  Decided on the device; read back with the prune counter.
+        S = self.model.num_segments
+        used = None
+        if S > 1:
+            used = active_segments(self.model.frame_numbers_to_segment_numbers, frames, S).to(torch.int64)
+            if self.world > 1:                       # a segment is active if any rank's batch touches it
+                dist.all_reduce(used, op=dist.ReduceOp.MAX, group=self.pg)
+        active = None
         # ---- prune_samples (volume_rendering.py:42-84): jitter, density-only pass, visibility compaction
         if self.prune:
             t = t + torch.rand(t.shape, device=dev, generator=self.gen) * step
@@ -101,11 +114,17 @@ class FusedTrainer:
                                   1e-4, keep.data_ptr(), kept_off.data_ptr(), t2.data_ptr(), ri2.data_ptr(),
                                   counter.data_ptr(), L.stream()))
             mark("prune_enqueued")
-            kept = int(counter.item())
+            if used is None:
+                kept = int(counter.item())
+            else:                                    # one read for both
+                host = torch.cat((counter, used)).cpu().tolist()
+                kept, active = int(host[0]), [bool(x) for x in host[1:]]
             t, ri = t2[:kept], ri2[:kept]
             launches += 9
             mark("prune_synced")
             off = kept_off                                   # hrf_prune's scan IS the ray-offset table of the survivors
+        if used is not None and active is None:
+            active = [bool(x) for x in used.cpu().tolist()]
         n = t.shape[0]
         # ---- forward: fused field + compositing
         samples = nat.samples_rays(o, d, frames, t, ri, cameras if self.model.camera_embedding_dim > 0 else None)
@@ -166,7 +185,7 @@ class FusedTrainer:
         if bwd_events is not None:
             bwd_events[1].record()
         mark("backward")
-        self.apply_adam(1.0 / self.world, works)
+        self.apply_adam(1.0 / self.world, works, active)
         launches += len(self.params) + 3
         mark("allreduce+adam")
         self.last = {"samples": n, "loss": loss.detach()}
@@ -177,12 +196,14 @@ class FusedTrainer:
             return float(loss.item())
         return launches
 
-    def apply_adam(self, grad_scale: float, works=None) -> None:
+    def apply_adam(self, grad_scale: float, works=None, active=None) -> None:
         """Adam over the bucket in region order; `works` = the 5 pending all-reduces (one per region), each waited for
-        just before the first parameter of its region is updated."""
+        just before the first parameter of its region.  `active` (bool per segment, None = all) selects the segments
+        that took part in this step: the others are skipped entirely and keep their own step counters, exactly what
+        torch.optim.Adam does with parameters whose .grad is None (the reference's trainer.py:174,251)."""
         nat = self.nat
-        self.t += 1
         lr = self.current_lr()
+        self.t += 1
         S = self.model.num_segments
         with torch.no_grad():
             for j, i in enumerate(self.adam_order):
@@ -190,6 +211,9 @@ class FusedTrainer:
                 if works is not None and works[region] is not None:
                     works[region].wait()
                     works[region] = None
+                if active is not None and i < 5 * S and not active[i // 5]:
+                    continue
+                self.steps[i] += 1
                 shadow = nat.shadows[i // 5][i % 5] if (i < 5 * S and i % 5 < 4) else None
                 self._adam(i, shadow, lr, grad_scale)
             nat.repack_mlp()
@@ -199,4 +223,4 @@ class FusedTrainer:
         a, b = self.slices[i]
         L.check(L.lib().hrf_adam_step(p.data_ptr(), self.exp_avg[a:b].data_ptr(), self.exp_avg_sq[a:b].data_ptr(),
                                       self.grad[a:b].data_ptr(), L.ptr(shadow), b - a, lr, self.betas[0], self.betas[1],
-                                      self.eps, self.t, grad_scale, L.stream()))
+                                      self.eps, self.steps[i], grad_scale, L.stream()))

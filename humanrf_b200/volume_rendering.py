@@ -87,7 +87,7 @@ class _RenderFunction(torch.autograd.Function):
     """field forward (ray-batch form) + compositing; backward = composite bwd + fused field bwd."""
 
     @staticmethod
-    def forward(ctx, model: HumanRF, o, d, fr, t, ri, num_rays, background, step, cams, needs_grad, *params):
+    def forward(ctx, model: HumanRF, o, d, fr, t, ri, num_rays, background, step, cams, needs_grad, active, *params):
         nat = model.native()
         dev = t.device
         samples = nat.samples_rays(o, d, fr, t, ri, cams)
@@ -102,7 +102,7 @@ class _RenderFunction(torch.autograd.Function):
         L.check(L.lib().hrf_composite_forward(sigma.data_ptr(), rgb.data_ptr(), t.data_ptr(), off.data_ptr(), num_rays,
                                               float(step), L.ptr(bg), color.data_ptr(), wsum.data_ptr(), None,
                                               L.stream()))
-        ctx.model, ctx.num_rays, ctx.step = model, num_rays, float(step)
+        ctx.model, ctx.num_rays, ctx.step, ctx.active = model, num_rays, float(step), active
         ctx.bg = bg
         ctx.save_for_backward(o, d, fr, t, ri, sigma, rgb, off, feat if feat is not None else t,
                               cams if cams is not None else fr)
@@ -126,7 +126,11 @@ class _RenderFunction(torch.autograd.Function):
         params = model.hot_parameters()
         grads = [torch.zeros_like(p) for p in params]
         nat.backward(nat.samples_rays(o, d, fr, t, ri, cams if ctx.has_cams else None), d_sigma, d_rgb, feat, grads)
-        return (None,) * 11 + tuple(grads)
+        if ctx.active is not None:      # segments the batch did not touch get no gradient at all (None), as in the reference
+            from .parallel import mask_inactive_segment_grads
+
+            grads = mask_inactive_segment_grads(grads, ctx.active)
+        return (None,) * 12 + tuple(grads)
 
 
 def render(input_batch: InputBatch, scene_representation: HumanRF, background_rgb: torch.Tensor, is_training: bool,
@@ -140,6 +144,8 @@ def render(input_batch: InputBatch, scene_representation: HumanRF, background_rg
     params = scene_representation.hot_parameters()
     # (ctx.needs_input_grad ignores torch.no_grad(): decide here whether the backward buffers are worth saving)
     needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    # humanrf.py:162-179: only the segments of this batch's frames are run (and receive gradients)
+    active = scene_representation.active_segment_list(fr, ib.unique_frame_numbers) if needs_grad else None
     color, wsum = _RenderFunction.apply(scene_representation, o, d, fr, t, ri, ib.num_rays, background_rgb,
-                                        render_step_size, cams, needs_grad, *params)
+                                        render_step_size, cams, needs_grad, active, *params)
     return RenderOutput(color=color, weights_sum=wsum)

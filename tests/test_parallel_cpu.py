@@ -7,8 +7,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from humanrf_b200.parallel import (allreduce_bucket_, broadcast_parameters_, deal_round_robin, grid_major_bucket_layout,
-                                   shard_range, union_batch_loss_scale)
+from humanrf_b200.parallel import (active_segments, allreduce_bucket_, broadcast_parameters_, deal_round_robin,
+                                   grid_major_bucket_layout, mask_inactive_segment_grads, shard_range, union_batch_loss_scale)
 
 
 def test_shard_range_and_round_robin_cover_everything():
@@ -42,6 +42,68 @@ def test_grid_major_bucket_layout():
             assert inside == [5 * s + k for s in range(S)]
         # sigma net and colour net stay adjacent (the fused backward writes them as one block)
         assert slices[5 * S][1] == slices[5 * S + 1][0]
+
+
+def test_active_segments_and_gradient_masking():
+    """humanrf.py:162-179 + trainer.py:174: segments the batch's frames do not fall into take no part in the step."""
+    from oracle.field import frame_luts
+
+    frames = tuple(range(15, 15 + 6 + 12 + 6))
+    f2s, _ = frame_luts(frames, (6, 12, 6))
+    lut = torch.from_numpy(f2s)
+    assert active_segments(lut, torch.tensor([15, 16, 20]), 3).tolist() == [True, False, False]
+    assert active_segments(lut, torch.tensor([[33], [21]], dtype=torch.int32), 3).tolist() == [False, True, True]
+    assert active_segments(lut, torch.tensor([3, 14, 999, -1]), 3).tolist() == [False, False, False]   # no segment / out of range
+    assert active_segments(lut, torch.zeros(0, dtype=torch.int64), 3).tolist() == [False, False, False]
+    grads = list(range(5 * 3 + 2))
+    masked = mask_inactive_segment_grads(grads, [True, False, True])
+    assert masked[:5] == grads[:5] and masked[5:10] == [None] * 5 and masked[10:] == grads[10:]
+
+
+def test_trainer_adam_schedule_skips_inactive_segments_and_keeps_their_step_counters():
+    """FusedTrainer.apply_adam's control flow with the kernel call mocked: region waits happen once each and in order,
+    inactive segments are skipped, per-parameter step counters follow torch.optim.Adam's state['step']."""
+    from humanrf_b200.training import FusedTrainer
+
+    S = 3
+    sizes = [10] * (5 * S) + [3072, 7168]
+
+    class Work:
+        def __init__(self, log, r):
+            self.log, self.r = log, r
+
+        def wait(self):
+            self.log.append(("wait", self.r))
+
+    class Nat:
+        shadows = [[f"shadow{s}{k}" for k in range(4)] for s in range(S)]
+
+        def repack_mlp(self):
+            log.append(("repack",))
+
+    class Model:
+        num_segments = S
+
+    log = []
+    tr = FusedTrainer.__new__(FusedTrainer)
+    tr.slices, tr.regions, tr.adam_order = grid_major_bucket_layout(sizes, S)
+    tr.nat, tr.model, tr.t, tr.steps = Nat(), Model(), 0, [0] * len(sizes)
+    tr.lr, tr.lr_decay, tr.max_steps = 1e-2, 0.5, 100
+    tr._adam = lambda i, shadow, lr, gs: log.append(("adam", i, shadow, tr.steps[i]))
+    tr.apply_adam(0.5, [Work(log, r) for r in range(5)], active=[True, False, True])
+    tr.apply_adam(0.5, None, active=[False, True, True])
+    tr.apply_adam(0.5, None, active=None)
+    first = log[:log.index(("repack",))]
+    assert [e for e in first if e[0] == "wait"] == [("wait", r) for r in range(5)]
+    # region k's wait precedes every Adam of region k even when the region's first parameter is inactive
+    for k in range(4):
+        w = first.index(("wait", k))
+        assert all(first.index(e) > w for e in first if e[0] == "adam" and e[1] < 5 * S and e[1] % 5 == k)
+    done = sorted(e[1] for e in first if e[0] == "adam")
+    assert done == [0, 1, 2, 3, 4, 10, 11, 12, 13, 14, 15, 16]                 # segment 1 skipped, MLPs always
+    assert ("adam", 0, "shadow00", 1) in first and ("adam", 4, None, 1) in first   # grids refresh their shadow, vectors do not
+    assert tr.t == 3
+    assert tr.steps == [2] * 5 + [2] * 5 + [3] * 5 + [3, 3]                    # per-parameter counters
 
 
 def test_allreduce_helpers_are_no_ops_without_a_process_group():

@@ -51,3 +51,63 @@ def test_prune_path_runs(cuda):
         loss = tr.step(g["o"], g["d"], g["frames"], g["t"], g["ri"], g["rgba"], 256, return_loss=True)
         assert np.isfinite(loss)
     assert 0 < tr.last["samples"] <= g["t"].shape[0]
+
+
+def test_multi_segment_steps_follow_the_reference_optimizer(cuda):
+    """Three temporal segments, batches that touch only some of them.  The reference runs only the touched segments
+    (humanrf.py:162-179), zero_grad(set_to_none=True) leaves the others' .grad at None (trainer.py:174) and
+    torch.optim.Adam then skips them, per-parameter step counters included.  Checked: the autograd route hands None to
+    the untouched segments; FusedTrainer leaves them bit-identical and counts their steps separately; after a few
+    mixed steps both routes agree with each other."""
+    from humanrf_b200.synthetic import input_batch_of
+    from humanrf_b200.training import FusedTrainer
+    from humanrf_b200.volume_rendering import render
+    from oracle import rendering as R
+
+    sizes = (6, 6, 6)
+    ma, frames = make_model(sizes, table_std=0.5, device=cuda)
+    mb, _ = make_model(sizes, table_std=0.5, device=cuda)
+    for p, q in zip(ma.hot_parameters(), mb.hot_parameters()):
+        assert torch.equal(p, q)
+    init = [p.detach().clone() for p in ma.hot_parameters()]
+    seg_frames = [frames[0:6], frames[6:12], frames[12:18]]
+    plans = [(0, 2), (1,), (0, 1, 2), (2,)]                       # segments each step's batch draws its frames from
+    opt = torch.optim.Adam(ma.get_params(1e-2), betas=(0.9, 0.99), eps=1e-15)       # run.py:101
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda k: 0.5 ** min(k / 50001, 1))
+    tr = FusedTrainer(mb, lr=1e-2, prune=False)
+    counts = [0, 0, 0]
+    for step, segs in enumerate(plans):
+        fr = tuple(f for s_ in segs for f in seg_frames[s_])
+        b = synthetic_rays(256, 48, fr, seed=30 + step, n_distinct_frames=len(fr))
+        touched = sorted({int(ma.frame_numbers_to_segment_numbers[f]) for f in b["frames"].tolist()})
+        assert set(touched) <= set(segs) and touched, touched
+        for s_ in touched:
+            counts[s_] += 1
+        bg = torch.rand(256, 3, generator=torch.Generator().manual_seed(step)).to(cuda)
+        # --- the reference's loop on the autograd route
+        opt.zero_grad(set_to_none=True)
+        ib = input_batch_of(b, cuda)
+        out = render(ib, ma, bg, is_training=True)
+        loss, _ = R.training_loss(out.color, out.weights_sum, ib.rgba, bg)
+        loss.backward()
+        for s_ in range(3):
+            got_none = [p.grad is None for p in ma.hot_parameters()[5 * s_:5 * s_ + 5]]
+            assert got_none == [s_ not in touched] * 5, (step, s_, got_none)
+        assert all(p.grad is not None for p in ma.hot_parameters()[15:])
+        opt.step()
+        sched.step()
+        # --- the fused trainer
+        g = {k: v.to(cuda).contiguous() for k, v in b.items() if k in ("o", "d", "frames", "t", "ri", "rgba")}
+        before = [p.detach().clone() for p in mb.hot_parameters()]
+        lf = tr.step(g["o"], g["d"], g["frames"], g["t"], g["ri"], g["rgba"], 256, return_loss=True, background=bg)
+        assert abs(lf - loss.item()) < 1e-3 * max(1.0, abs(lf)), (step, lf, loss.item())
+        for s_ in range(3):
+            same = [torch.equal(p.detach(), q) for p, q in zip(mb.hot_parameters()[5 * s_:5 * s_ + 5], before[5 * s_:5 * s_ + 5])]
+            assert same == [s_ not in touched] * 5, (step, s_, same)
+    assert tr.steps == [c for c in counts for _ in range(5)] + [len(plans)] * 2 and tr.t == len(plans)
+    for i, (p, q, p0) in enumerate(zip(ma.hot_parameters(), mb.hot_parameters(), init)):
+        moved = (p.detach() - p0).norm().item()
+        rel = (p.detach() - q.detach()).norm().item() / max(moved, 1e-12)
+        outliers = ((p.detach() - q.detach()).abs() > 2e-3).float().mean().item()
+        print(f"param {i}: moved {moved:.3e} rel diff {rel:.3e} outliers {outliers:.2e}")
+        assert rel < 2e-2 and outliers < 2e-3, (i, rel, outliers)
