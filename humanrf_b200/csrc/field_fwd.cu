@@ -278,6 +278,7 @@ static int launch_field_forward(const FieldArgs& a, int mlp_impl, cudaStream_t s
   else if (a.egrid != nullptr) rc = launch(field_forward_kernel<false, 5, true>);   // training forward: also saves e_k
   else if (ctas == 5 && unroll == 2) rc = launch(field_forward_kernel<false, 5, false, 2>);
   else if (ctas == 5 && unroll == 1) rc = launch(field_forward_kernel<false, 5, false, 1>);
+  else if (ctas == 6 && unroll == 1 && ctas_forced) rc = launch(field_forward_kernel<false, 6, false, 1>);   // round-2 experiment
   else if (ctas == 6) rc = launch(field_forward_kernel<false, 6>);
   else if (ctas == 4) rc = launch(field_forward_kernel<false, 4>);
   else rc = launch(field_forward_kernel<false, 5>);
