@@ -104,6 +104,23 @@ def cpu_oracle_rate(steps=3, warmup=1, rays_per_worker=16):
     return r["rays_per_s"], r["cores"], r["sample"], r
 
 
+def companion_line(mode, steps):
+    """`bench.py --mode <mode>` in a fresh process; returns the headline fields of its JSON line (or the failure)."""
+    cmd = [sys.executable, str(ROOT / "bench.py"), "--mode", mode, "--steps", str(steps), "--warmup", "3", "--no-cpu-baseline",
+           "--no-companions"]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        full = json.loads([ln for ln in r.stdout.strip().splitlines() if ln.startswith("{")][-1])
+        keep = {k: full.get(k) for k in ("metric", "value", "unit", "steps", "warmup", "ms_per_step", "gpu_launches")}
+        keep["e2e"] = (full.get("e2e") or {}).get("value")
+        keep["workload"] = (full.get("config") or {}).get("workload")
+        if full.get("roofline"):
+            keep["roofline_frac"], keep["roofline_kernel"] = full["roofline"].get("frac"), full["roofline"].get("kernel")
+        return keep
+    except Exception as e:  # noqa: BLE001 -- the render line must still be printed
+        return {"error": f"{type(e).__name__}: {e}"[:300]}
+
+
 def run_reference(args):
     rank, world, _ = dist_info()
     if rank != 0:
@@ -181,6 +198,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default="render", choices=["render", "train", "image"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-companions", action="store_true",
+                    help="do not append the train / full-image numbers to the default render line")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -383,6 +402,11 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             v, cores, sample, _ = cpu_oracle_rate(steps=3, warmup=1, rays_per_worker=16)
             line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample}
+        if world == 1 and args.mode == "render" and not args.no_companions:
+            # BASELINE.json's metric is a pair ("train rays/sec & render Mpix/s"): the default line measures the fused
+            # render kernel chain on north_star's 4096 x 512 batch; the other two workloads run right after it (each in
+            # its own process, own timed region, same rules) and are attached here so one run reports all three.
+            line["companions"] = {m: companion_line(m, k) for m, k in (("train", args.steps), ("image", 3))}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
