@@ -109,7 +109,7 @@ def companion_line(mode, steps):
     cmd = [sys.executable, str(ROOT / "bench.py"), "--mode", mode, "--steps", str(steps), "--warmup", "3", "--no-cpu-baseline",
            "--no-companions"]
     try:
-        r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=150)
         full = json.loads([ln for ln in r.stdout.strip().splitlines() if ln.startswith("{")][-1])
         keep = {k: full.get(k) for k in ("metric", "value", "unit", "steps", "warmup", "ms_per_step", "gpu_launches")}
         keep["e2e"] = (full.get("e2e") or {}).get("value")
