@@ -73,6 +73,28 @@ def mask_inactive_segment_grads(grads: List, active: Sequence[bool]) -> List:
     return out
 
 
+def _merge_spans(spans):
+    out = []
+    for a, b in sorted(spans):
+        if out and out[-1][1] == a:
+            out[-1] = (out[-1][0], b)
+        elif b > a:
+            out.append((a, b))
+    return out
+
+
+def allreduce_spans(slices, regions, num_segments: int, active=None):
+    """What has to cross NVLink in one step: for each of the 5 bucket regions (grid 0..3 of every segment, then the tail)
+    the contiguous spans holding gradients of ACTIVE segments (a batch touches <= 8 frames, i.e. typically one
+    or two segments); the MLP / embedding block at the end of the tail always takes part.  With active=None every
+    region is one span (single-segment models, or a batch touching every segment)."""
+    S = num_segments
+    on = [True] * S if active is None else list(active)
+    out = [_merge_spans([slices[5 * s + k] for s in range(S) if on[s]]) for k in range(4)]
+    out.append(_merge_spans([slices[5 * s + 4] for s in range(S) if on[s]] + [(slices[5 * S][0], regions[4][1])]))
+    return out
+
+
 def union_batch_loss_scale(num_rays_local: int, device, group=None):
     """world * R_local / R_total, so that summing rank gradients and dividing by world gives the gradient of the
     mean loss over the union of all ranks' rays.  One 8-byte all-reduce; the result stays ON THE DEVICE (a 0-dim

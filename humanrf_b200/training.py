@@ -22,7 +22,8 @@ import torch
 import torch.distributed as dist
 
 from . import _lib as L
-from .parallel import active_segments, allreduce_bucket_, grid_major_bucket_layout, union_batch_loss_scale
+from .parallel import (active_segments, allreduce_bucket_, allreduce_spans, grid_major_bucket_layout,
+                       union_batch_loss_scale)
 from .scene_representation.humanrf import HumanRF
 from .volume_rendering import ray_offsets
 
@@ -166,22 +167,28 @@ class FusedTrainer:
                                            L.stream()))
         egrid = feat.data_ptr() + 64 * n
         works = None
+        # data parallel: only the gradients of the segments this step touched (on any rank) are reduced
+        spans = allreduce_spans(self.slices, self.regions, S, active) if self.world > 1 else None
         if self.world == 1 or not self.overlap_allreduce:
             L.check(lib.hrf_field_backward_tables(C.byref(nat.field), C.byref(samples), self.sg_dev.data_ptr(), egrid,
                                                   ws.data_ptr(), 0, 4, L.stream()))
-            if self.world > 1:
-                allreduce_bucket_(self.grad, self.pg)
-            launches += 8 + 12 + (1 if self.world > 1 else 0)
+            if self.world > 1 and active is None:
+                allreduce_bucket_(self.grad, self.pg)                       # everything is active: one message
+            elif self.world > 1:
+                for region in spans:
+                    for a, b in region:
+                        allreduce_bucket_(self.grad[a:b], self.pg)
+            launches += 8 + 12 + ((1 if active is None else sum(len(r) for r in spans)) if self.world > 1 else 0)
         else:
-            # data parallel: table k's gradient region is reduced (NCCL, its own stream) while table k+1 is still being
-            # scattered; the sum's mean over ranks is folded into Adam's grad_scale
+            # table k's gradient region is reduced (NCCL, its own stream) while table k+1 is still being scattered; the
+            # sum's mean over ranks is folded into Adam's grad_scale
             works = []
             for k in range(4):
                 L.check(lib.hrf_field_backward_tables(C.byref(nat.field), C.byref(samples), self.sg_dev.data_ptr(), egrid,
                                                       ws.data_ptr(), k, 1, L.stream()))
-                works.append(allreduce_bucket_(self.grad[self.regions[k][0]:self.regions[k][1]], self.pg, async_op=True))
-            works.append(allreduce_bucket_(self.grad[self.regions[4][0]:self.regions[4][1]], self.pg, async_op=True))
-            launches += 8 + 15 + 5
+                works.append([allreduce_bucket_(self.grad[a:b], self.pg, async_op=True) for a, b in spans[k]])
+            works.append([allreduce_bucket_(self.grad[a:b], self.pg, async_op=True) for a, b in spans[4]])
+            launches += 8 + 15 + sum(len(r) for r in spans)
         if bwd_events is not None:
             bwd_events[1].record()
         mark("backward")
@@ -197,8 +204,8 @@ class FusedTrainer:
         return launches
 
     def apply_adam(self, grad_scale: float, works=None, active=None) -> None:
-        """Adam over the bucket in region order; `works` = the 5 pending all-reduces (one per region), each waited for
-        just before the first parameter of its region.  `active` (bool per segment, None = all) selects the segments
+        """Adam over the bucket in region order; `works` = the pending all-reduces of each of the 5 regions (a list per
+        region), waited for just before the first parameter of that region.  `active` (bool per segment, None = all) selects the segments
         that took part in this step: the others are skipped entirely and keep their own step counters, exactly what
         torch.optim.Adam does with parameters whose .grad is None (the reference's trainer.py:174,251)."""
         nat = self.nat
@@ -208,9 +215,10 @@ class FusedTrainer:
         with torch.no_grad():
             for j, i in enumerate(self.adam_order):
                 region = min(j // S, 4)
-                if works is not None and works[region] is not None:
-                    works[region].wait()
-                    works[region] = None
+                if works is not None and works[region]:
+                    for w in works[region]:
+                        w.wait()
+                    works[region] = []
                 if active is not None and i < 5 * S and not active[i // 5]:
                     continue
                 self.steps[i] += 1

@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from humanrf_b200.parallel import (active_segments, allreduce_bucket_, broadcast_parameters_, deal_round_robin,
+from humanrf_b200.parallel import (active_segments, allreduce_bucket_, allreduce_spans, broadcast_parameters_, deal_round_robin,
                                    grid_major_bucket_layout, mask_inactive_segment_grads, shard_range, union_batch_loss_scale)
 
 
@@ -42,6 +42,31 @@ def test_grid_major_bucket_layout():
             assert inside == [5 * s + k for s in range(S)]
         # sigma net and colour net stay adjacent (the fused backward writes them as one block)
         assert slices[5 * S][1] == slices[5 * S + 1][0]
+
+
+def test_allreduce_spans_cover_exactly_the_active_gradients():
+    for S in (1, 2, 4):
+        sizes = []
+        for s in range(S):
+            sizes += [100 + s, 200 + s, 300 + s, 400 + s, 50 + s]
+        sizes += [3072, 7168, 320]
+        slices, regions, _ = grid_major_bucket_layout(sizes, S)
+        # nothing to decide: one span per region, together the whole bucket
+        assert allreduce_spans(slices, regions, S, None) == [[r] for r in regions]
+        assert allreduce_spans(slices, regions, S, [True] * S) == [[r] for r in regions]
+        for active in ([False] * S, [s % 2 == 0 for s in range(S)], [s == S - 1 for s in range(S)]):
+            spans = allreduce_spans(slices, regions, S, active)
+            covered = torch.zeros(regions[-1][1], dtype=torch.int32)
+            for k, region in enumerate(spans):
+                for a, b in region:
+                    assert regions[k][0] <= a < b <= regions[k][1]        # spans stay inside their region
+                    covered[a:b] += 1
+            want = torch.zeros_like(covered)
+            for i, (a, b) in enumerate(slices):
+                if i >= 5 * S or active[i // 5]:
+                    want[a:b] = 1
+            assert torch.equal(covered, want)                              # every active gradient once, nothing else
+            assert all(x[1] < y[0] for region in spans for x, y in zip(region, region[1:]))   # merged: no touching spans
 
 
 def test_active_segments_and_gradient_masking():
@@ -90,7 +115,7 @@ def test_trainer_adam_schedule_skips_inactive_segments_and_keeps_their_step_coun
     tr.nat, tr.model, tr.t, tr.steps = Nat(), Model(), 0, [0] * len(sizes)
     tr.lr, tr.lr_decay, tr.max_steps = 1e-2, 0.5, 100
     tr._adam = lambda i, shadow, lr, gs: log.append(("adam", i, shadow, tr.steps[i]))
-    tr.apply_adam(0.5, [Work(log, r) for r in range(5)], active=[True, False, True])
+    tr.apply_adam(0.5, [[Work(log, r)] for r in range(5)], active=[True, False, True])
     tr.apply_adam(0.5, None, active=[False, True, True])
     tr.apply_adam(0.5, None, active=None)
     first = log[:log.index(("repack",))]
