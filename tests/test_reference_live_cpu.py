@@ -1,0 +1,166 @@
+"""Differential tests against the LIVE reference (imported read-only from /root/reference) on randomized inputs, for the
+first-party pure-Python pieces of the path.  They complement the frozen goldens of tests/golden/ (which also run on the
+GPU box, where the reference does not exist): here every run draws many more cases.  Skipped when the reference is
+not mounted."""
+import dataclasses
+import sys
+import types
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+REF = Path("/root/reference")
+pytestmark = pytest.mark.skipif(not REF.exists(), reason="reference checkout not present (GPU box)")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    """The reference's importable modules.  Imported under their own names, so anything of ours that was shadowed is
+    restored afterwards."""
+    saved = {k: v for k, v in sys.modules.items() if k.split(".")[0] in ("humanrf", "actorshq")}
+    for k in saved:
+        del sys.modules[k]
+    sys.path.insert(0, str(REF))
+    try:
+        import actorshq.dataset.input_batch as ib
+        import humanrf.input as inp
+        import humanrf.scene_representation.query_io as qio
+        import humanrf.utils.activation as act
+        import humanrf.utils.loss as loss
+        # adaptive_temporal_partitioning imports VolumetricDataset only for an annotation (needs cv2 etc.): stub it
+        if "actorshq.dataset.volumetric_dataset" not in sys.modules:
+            stub = types.ModuleType("actorshq.dataset.volumetric_dataset")
+            stub.VolumetricDataset = object
+            sys.modules["actorshq.dataset.volumetric_dataset"] = stub
+        import humanrf.adaptive_temporal_partitioning as atp
+        yield types.SimpleNamespace(ib=ib, inp=inp, qio=qio, act=act, loss=loss, atp=atp)
+    finally:
+        sys.path.remove(str(REF))
+        for k in [k for k in sys.modules if k.split(".")[0] in ("humanrf", "actorshq")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+
+
+def _surface(cls):
+    fields = [(f.name, f.default) for f in dataclasses.fields(cls)]
+    return fields, sorted(m for m in dir(cls) if not m.startswith("_"))
+
+
+def test_dataclass_surfaces_match(ref):
+    from humanrf_b200.dataset.input_batch import InputBatch
+    from humanrf_b200.scene_representation.query_io import QueryInput, QueryOutput
+
+    assert _surface(InputBatch) == _surface(ref.ib.InputBatch)
+    assert _surface(QueryInput) == _surface(ref.qio.QueryInput)
+    assert _surface(QueryOutput) == _surface(ref.qio.QueryOutput)
+
+
+FIELDS = ["ray_origins", "ray_directions", "minmaxes", "rgba", "ray_masks", "frame_numbers", "unique_frame_numbers",
+          "camera_numbers", "sample_distances", "ray_indices"]
+
+
+def _batch(cls, rng, num_rays, masked):
+    counts = rng.integers(0, 9, num_rays)
+    ri = np.repeat(np.arange(num_rays), counts)
+    mask = np.ones((num_rays + masked, 1), bool)
+    mask[rng.permutation(num_rays + masked)[:masked]] = False
+    fr = rng.integers(15, 40, (num_rays, 1)).astype(np.int32)
+    t = torch.from_numpy
+    return cls(ray_origins=t(rng.normal(size=(num_rays, 3)).astype(np.float32)),
+               ray_directions=t(rng.normal(size=(num_rays, 3)).astype(np.float32)),
+               minmaxes=t(rng.random((num_rays, 2)).astype(np.float32)), rgba=t(rng.random((num_rays, 4)).astype(np.float32)),
+               ray_masks=t(mask), frame_numbers=t(fr), unique_frame_numbers=torch.unique(t(fr)).view(-1, 1),
+               camera_numbers=t(rng.integers(0, 160, (num_rays, 1)).astype(np.int32)),
+               sample_distances=t(rng.random((int(counts.sum()), 1)).astype(np.float32)), ray_indices=t(ri.astype(np.int64)),
+               width=64, height=48)
+
+
+def test_merge_input_batches_randomized(ref):
+    """input.py:10-55 incl. the sample-budget cut-off and its `cumsum < cutoff` behaviour, 60 random configurations."""
+    from humanrf_b200.dataset.input_batch import InputBatch
+    from humanrf_b200.input import merge_input_batches
+
+    rng = np.random.default_rng(7)
+    checked_cut = 0
+    for case in range(60):
+        nb = int(rng.integers(1, 5))
+        specs = [(int(rng.integers(1, 30)), int(rng.integers(0, 5))) for _ in range(nb)]
+        seed = int(rng.integers(0, 2 ** 31))
+        total = None
+        outs = []
+        for cls, fn in ((ref.ib.InputBatch, ref.inp.merge_input_batches), (InputBatch, merge_input_batches)):
+            r2 = np.random.default_rng(seed)
+            batches = [_batch(cls, r2, *s) for s in specs]
+            total = sum(b.sample_distances.shape[0] for b in batches)
+            budget = [None, max(1, total // 2), max(1, total - 1), total, total + 5, 1][case % 6]
+            outs.append(fn(batches, budget))
+        a, b = outs
+        if budget is not None and budget < total:
+            checked_cut += 1
+        for f in FIELDS:
+            x, y = getattr(a, f), getattr(b, f)
+            if f == "unique_frame_numbers":
+                x, y = torch.sort(x.reshape(-1))[0], torch.sort(y.reshape(-1))[0]
+            assert x.dtype == y.dtype and x.shape == y.shape and torch.equal(x, y), (case, f)
+        assert (a.width, a.height) == (b.width, b.height)
+    assert checked_cut >= 15
+
+
+def test_truncated_exp_and_bce_randomized(ref):
+    from humanrf_b200.utils.activation import truncated_exp
+    from humanrf_b200.utils.loss import bce_loss
+
+    g = torch.Generator().manual_seed(3)
+    for scale in (1.0, 9.0, 30.0):
+        x = torch.randn(513, generator=g) * scale
+        dy = torch.randn(513, generator=g)
+        outs = []
+        for fn in (ref.act.truncated_exp, truncated_exp):
+            xi = x.clone().requires_grad_(True)
+            y = fn(xi)
+            y.backward(dy)
+            outs.append((y.detach(), xi.grad))
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    pred = torch.rand(777, 1, generator=g) * 1.6 - 0.3
+    target = (torch.rand(777, 1, generator=g) > 0.4).float()
+    assert torch.equal(ref.loss.bce_loss(pred, target), bce_loss(pred, target))
+
+
+def test_segment_size_rules_and_partitioning_randomized(ref):
+    """adaptive_temporal_partitioning.py:28-107 against the oracle restatement (the GPU implementation is compared with
+    the same reference decisions through tests/golden/partitioning.npz)."""
+    from humanrf_b200 import adaptive_temporal_partitioning as ours
+    from oracle import occupancy_tools as O
+
+    assert ours.PREDEFINED_SEGMENT_SIZES == ref.atp.PREDEFINED_SEGMENT_SIZES == O.PREDEFINED_SEGMENT_SIZES
+    for n in range(1, 260):
+        assert ours.get_segment_size(n) == ref.atp.get_segment_size(n) == O.get_segment_size(n)
+        assert ours.get_final_segment_size(n) == ref.atp.get_final_segment_size(n) == O.get_final_segment_size(n)
+
+    class DS:
+        def __init__(self, grids):
+            self.grids = grids
+
+        def get_occupancy_grid(self, frame_number):
+            return self.grids[frame_number].copy()       # the reference ORs into the first grid of a cluster in place
+
+    rng = np.random.default_rng(11)
+    for case in range(12):
+        n = int(rng.integers(3, 140))
+        base = rng.random((12, 12, 12)) < 0.2
+        grids, cur = [], base.copy()
+        for f in range(n):
+            if rng.random() < [0.05, 0.3, 0.8][case % 3]:
+                cur = cur | (rng.random(cur.shape) < 0.02)    # occasional growth of the occupied set
+            if rng.random() < 0.03:
+                cur = rng.random(cur.shape) < 0.2             # a jump
+            grids.append((cur * 255).astype(np.uint8))
+        thr = [1.05, 1.25, 2.0][case % 3]
+        import contextlib
+        import io
+
+        with contextlib.redirect_stderr(io.StringIO()):      # tqdm bar
+            want = ref.atp.compute_adaptive_segment_sizes(DS(grids), list(range(n)), thr)
+        assert O.compute_adaptive_segment_sizes(grids, thr) == want, case
