@@ -164,3 +164,98 @@ def test_segment_size_rules_and_partitioning_randomized(ref):
         with contextlib.redirect_stderr(io.StringIO()):      # tqdm bar
             want = ref.atp.compute_adaptive_segment_sizes(DS(grids), list(range(n)), thr)
         assert O.compute_adaptive_segment_sizes(grids, thr) == want, case
+
+
+_MODEL_CACHE = {}
+
+
+def _import_reference_model():
+    """The reference's HumanRF with `tinycudann` and its compiled extension stubbed out: the stubs only RECORD the
+    configs they are constructed with and own one flat `.params` (sized by our layout rule -- sizes of tcnn tensors are
+    therefore not evidence, the configs / names / first-party tensors are)."""
+    from humanrf_b200.scene_representation.grid_layout import GridLayout, MLP_SIGMA_PARAMS, mlp_color_params
+
+    if _MODEL_CACHE:                       # the module stays bound to the stub classes (and their log) of its first import
+        _MODEL_CACHE["calls"].clear()
+        sys.modules["tinycudann"] = _MODEL_CACHE["tcnn"]
+        sys.modules["humanrf.scene_representation.humanrf"] = _MODEL_CACHE["module"]
+        return _MODEL_CACHE["module"], _MODEL_CACHE["calls"]
+    calls = []
+
+    class _Flat(torch.nn.Module):
+        def __init__(self, n):
+            super().__init__()
+            self.params = torch.nn.Parameter(torch.zeros(n))
+
+    class Encoding(_Flat):
+        def __init__(self, n_input_dims, encoding_config, **kw):
+            calls.append(("Encoding", n_input_dims, dict(encoding_config)))
+            c = encoding_config
+            fin = c["base_resolution"] * c["per_level_scale"] ** (c["n_levels"] - 1)
+            super().__init__(GridLayout(c["log2_hashmap_size"], c["n_levels"], c["base_resolution"], int(round(fin))).n_params)
+
+    class Network(_Flat):
+        def __init__(self, n_input_dims, n_output_dims, network_config, **kw):
+            calls.append(("Network", n_input_dims, n_output_dims, dict(network_config)))
+            super().__init__(MLP_SIGMA_PARAMS)
+
+    class NetworkWithInputEncoding(_Flat):
+        def __init__(self, n_input_dims, n_output_dims, encoding_config, network_config, **kw):
+            calls.append(("NetworkWithInputEncoding", n_input_dims, n_output_dims, dict(encoding_config), dict(network_config)))
+            super().__init__(mlp_color_params(n_input_dims - 18))
+
+    tcnn = types.ModuleType("tinycudann")
+    tcnn.Encoding, tcnn.Network, tcnn.NetworkWithInputEncoding = Encoding, Network, NetworkWithInputEncoding
+    sys.modules["tinycudann"] = tcnn
+    sys.modules["humanrf.scene_representation.tensor_composition_native"] = types.ModuleType("tensor_composition_native")
+    import humanrf.scene_representation.humanrf as ref_model
+
+    _MODEL_CACHE.update(module=ref_model, calls=calls, tcnn=tcnn)
+    return ref_model, calls
+
+
+@pytest.mark.parametrize("segment_sizes,first,count,cam_emb", [((50,), 15, 50, 0), ((25, 12, 100, 6), 0, 140, 2), ((6, 6), 3, 9, 0)])
+def test_model_constructor_against_the_reference(ref, segment_sizes, first, count, cam_emb):
+    """humanrf.py:68-156 + decomposition4d.py:73-122 run for real (only tcnn is a recording stub): frame LUTs, per-segment
+    hash-map sizes, encoding / network configs, state-dict key names and the shapes of the first-party tensors."""
+    from humanrf_b200.scene_representation.grid_layout import GridLayout
+    from humanrf_b200.scene_representation.humanrf import HumanRF
+    from humanrf_b200.synthetic import MODEL_KW
+
+    try:
+        ref_model, calls = _import_reference_model()
+        frames = tuple(range(first, first + count))
+        kw = {**MODEL_KW, "camera_embedding_dim": cam_emb, "temporal_partitioning": "adaptive", "fixed_segment_size": 6}
+        theirs = ref_model.HumanRF(sorted_frame_numbers=frames, segment_sizes=segment_sizes, **kw)
+        ours = HumanRF(sorted_frame_numbers=frames, segment_sizes=segment_sizes, **kw)
+    finally:
+        sys.modules.pop("tinycudann", None)
+    # frame -> segment / local-time look-up tables
+    assert torch.equal(ours.frame_numbers_to_segment_numbers, theirs.frame_numbers_to_segment_numbers)
+    assert torch.equal(ours.frame_numbers_to_normalized_local_frame_numbers, theirs.frame_numbers_to_normalized_local_frame_numbers)
+    assert (ours.num_frames, ours.num_segments, ours.total_feature_dim, ours.density_scale) == \
+           (theirs.num_frames, theirs.num_segments, theirs.total_feature_dim, theirs.density_scale)
+    # what the reference asks tcnn for, segment by segment
+    enc = [c for c in calls if c[0] == "Encoding"]
+    assert len(enc) == 4 * len(segment_sizes)
+    for s, fg in enumerate(ours.feature_grids):
+        for c in enc[4 * s:4 * s + 4]:
+            cfg = c[2]
+            assert c[1] == 3 and cfg["otype"] == "HashGrid" and cfg["n_levels"] == 16 and cfg["n_features_per_level"] == 2
+            assert cfg["log2_hashmap_size"] == fg.layout.log2_hashmap_size
+            assert cfg["base_resolution"] == 32 and np.float32(cfg["per_level_scale"]) == np.float32(np.exp(np.log(2048 / 32) / 15))
+            assert GridLayout(cfg["log2_hashmap_size"]).n_params == fg.layout.n_params
+    net = [c for c in calls if c[0] == "Network"][0]
+    assert net[1:3] == (32, 16) and net[3] == {"otype": "FullyFusedMLP", "activation": "ReLU", "output_activation": "None",
+                                              "n_neurons": 64, "n_hidden_layers": 1}
+    col = [c for c in calls if c[0] == "NetworkWithInputEncoding"][0]
+    assert col[1:3] == (18 + cam_emb, 3) and col[4]["output_activation"] == "Sigmoid" and col[4]["n_hidden_layers"] == 2
+    assert col[3]["nested"][0] == {"n_dims_to_encode": 3, "otype": "SphericalHarmonics", "degree": 4}
+    # state dict: same keys in the same order, same shapes (first-party tensors: vectors, LUT buffers, embeddings)
+    a, b = ours.state_dict(), theirs.state_dict()
+    assert list(a.keys()) == list(b.keys())
+    for k in a:
+        assert a[k].shape == b[k].shape and a[k].dtype == b[k].dtype, k
+    # optimiser parameter groups (humanrf.py:210-220)
+    ga, gb = ours.get_params(1e-2), theirs.get_params(1e-2)
+    assert [len(list(g["params"])) for g in ga] == [len(list(g["params"])) for g in gb] and [g["lr"] for g in ga] == [g["lr"] for g in gb]
