@@ -36,7 +36,7 @@ class RenderOutput:
         for key, val in vars(render_outputs[0]).items():
             if isinstance(val, torch.Tensor):
                 setattr(out, key, torch.cat([getattr(r, key) for r in render_outputs], dim=0))
-            elif val is not None:
+            else:   # as the reference (volume_rendering.py:30-37): every field has to be a tensor, None included
                 raise RuntimeError("Unknown data type in the input_batches!")
         return out
 

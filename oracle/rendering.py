@@ -1,10 +1,13 @@
 """Oracle: transmittance / visibility / compositing / loss on the CPU.
 
 TEST INFRASTRUCTURE ONLY.  Follows humanrf/volume_rendering.py:42-150 and
-humanrf/trainer.py:205-255, humanrf/utils/loss.py:4-10.  PARITY UNPINNED for the
-nerfacc==0.3.1 pieces (requirements.txt:3, not under /root/reference): restated from its
-published semantics (nerfacc/vol_rendering.py: render_visibility,
-render_weight_from_density, accumulate_along_rays).
+humanrf/trainer.py:205-255, humanrf/utils/loss.py:4-10.  The first-party glue (positions,
+jitter, alpha, t_ends = t + step, mask application, background blend) is PINNED: the
+reference's own prune_samples / render run on the CPU and agree bit for bit
+(tests/test_reference_live_cpu.py).  PARITY UNPINNED for the nerfacc==0.3.1 pieces
+(requirements.txt:3, not under /root/reference): restated from its published semantics
+(nerfacc/vol_rendering.py: render_visibility, render_weight_from_density,
+accumulate_along_rays).
 """
 from __future__ import annotations
 

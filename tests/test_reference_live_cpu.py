@@ -259,3 +259,82 @@ def test_model_constructor_against_the_reference(ref, segment_sizes, first, coun
     # optimiser parameter groups (humanrf.py:210-220)
     ga, gb = ours.get_params(1e-2), theirs.get_params(1e-2)
     assert [len(list(g["params"])) for g in ga] == [len(list(g["params"])) for g in gb] and [g["lr"] for g in ga] == [g["lr"] for g in gb]
+
+
+def test_prune_and_render_glue_against_the_reference(ref):
+    """The reference's own prune_samples / render / merge_render_outputs (volume_rendering.py:26-150) executed on the CPU
+    with `nerfacc` replaced by the oracle's restatement of its three functions and a closed-form stand-in for the scene
+    representation: pins everything the oracle restates AROUND nerfacc (positions, jitter, alpha, t_ends = t + step,
+    mask application, background blend, output shapes).  nerfacc's own arithmetic stays unpinned."""
+    from helpers import synthetic_rays
+    from humanrf_b200.volume_rendering import RenderOutput as OurRenderOutput
+    from oracle import rendering as R
+
+    nerfacc = types.ModuleType("nerfacc")
+    nerfacc.render_visibility = lambda alphas, ray_indices, early_stop_eps, alpha_thre, n_rays: \
+        R.render_visibility(alphas, ray_indices, early_stop_eps, alpha_thre)
+
+    def render_weight_from_density(t_starts, t_ends, sigmas, ray_indices, n_rays):
+        sdt = sigmas.reshape(-1) * (t_ends - t_starts).reshape(-1)
+        return (torch.exp(-R._exclusive_by_ray(sdt, ray_indices, "sum")) * (1.0 - torch.exp(-sdt))).unsqueeze(-1)
+
+    nerfacc.render_weight_from_density = render_weight_from_density
+    nerfacc.accumulate_along_rays = lambda weights, ray_indices, values=None, n_rays=None: R.accumulate(weights, ray_indices, values, n_rays)
+    try:
+        _import_reference_model()
+        sys.modules["nerfacc"] = nerfacc
+        import humanrf.volume_rendering as vr
+    finally:
+        sys.modules.pop("tinycudann", None)
+        sys.modules.pop("nerfacc", None)
+    QueryOutput = ref.qio.QueryOutput
+
+    class Scene:
+        def density(self, q):
+            r2 = (q.positions ** 2).sum(1)
+            return QueryOutput(density=2500.0 * torch.exp(-60.0 * r2) * (1.0 + 0.25 * (q.frame_numbers.reshape(-1) % 3).float()))
+
+        def __call__(self, q):
+            return QueryOutput(density=self.density(q).density, radiance=torch.sigmoid(3.0 * q.positions + q.directions))
+
+    frames = tuple(range(15, 27))
+    b = synthetic_rays(64, 40, frames, ragged=True, seed=8)
+    o, d, fr, ri = b["o"], b["d"], b["frames"].view(-1, 1), b["ri"]
+
+    def batch(t):
+        return ref.ib.InputBatch(ray_origins=o, ray_directions=d, frame_numbers=fr, unique_frame_numbers=torch.unique(fr).view(-1, 1),
+                                 camera_numbers=torch.zeros_like(fr), sample_distances=t.clone().view(-1, 1), ray_indices=ri.clone(),
+                                 rgba=b["rgba"], width=8, height=8)
+
+    scene = Scene()
+    for is_training in (False, True):
+        ib = batch(b["t"])
+        torch.manual_seed(5)
+        vr.prune_samples(ib, scene, is_training=is_training)
+        torch.manual_seed(5)
+        t = b["t"].view(-1, 1) + (torch.rand_like(b["t"].view(-1, 1)) * R.STEP if is_training else 0)
+        pos = o[ri] + t * d[ri]
+        sigma = scene.density(types.SimpleNamespace(positions=pos, frame_numbers=fr[ri])).density
+        keep = R.prune_mask(sigma, ri)
+        assert 0 < int(keep.sum()) < keep.numel()
+        assert torch.equal(ib.sample_distances, t[keep]) and torch.equal(ib.ray_indices, ri[keep])
+        assert ib.sample_distances.shape == (int(keep.sum()), 1)
+        # render the survivors
+        bg = torch.rand(64, 3, generator=torch.Generator().manual_seed(1))
+        out = vr.render(ib, scene, bg, is_training=is_training)
+        tk, rk = t[keep], ri[keep]
+        pk = o[rk] + tk * d[rk]
+        q = types.SimpleNamespace(positions=pk, directions=d[rk], frame_numbers=fr[rk])
+        col, ws = R.render(tk, scene.density(q).density, scene(q).radiance, rk, 64, bg)
+        assert torch.equal(out.color, col) and torch.equal(out.weights_sum, ws)
+        assert out.color.shape == (64, 3) and out.weights_sum.shape == (64, 1)
+        nobg = vr.render(ib, scene, None, is_training=is_training)
+        assert torch.equal(nobg.color, R.render(tk, scene.density(q).density, scene(q).radiance, rk, 64, None)[0])
+    # merge_render_outputs: same concatenation, same error for a field that is not a tensor
+    parts = [vr.RenderOutput(color=torch.rand(n, 3), weights_sum=torch.rand(n, 1)) for n in (3, 0, 5)]
+    a = vr.RenderOutput.merge_render_outputs(parts)
+    c = OurRenderOutput.merge_render_outputs([OurRenderOutput(color=p.color, weights_sum=p.weights_sum) for p in parts])
+    assert torch.equal(a.color, c.color) and torch.equal(a.weights_sum, c.weights_sum)
+    for cls in (vr.RenderOutput, OurRenderOutput):
+        with pytest.raises(RuntimeError, match="Unknown data type"):
+            cls.merge_render_outputs([cls(color=torch.rand(2, 3))])
