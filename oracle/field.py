@@ -7,6 +7,10 @@ TEST INFRASTRUCTURE ONLY.  Follows
   humanrf/utils/activation.py:6-39                         (truncated_exp)
 and, PARITY UNPINNED (un-vendored tiny-cuda-nn): FullyFusedMLP layout/padding, the
 Composite[SphericalHarmonics(4), Identity] encoding padded to 32 with 1.0.
+The glue around the tcnn modules IS pinned: the reference's own HumanRF.__init__ / density /
+forward and Decomposition4D.forward run on the CPU with each tcnn module answering through
+this file's restatement of that module, and agree with OracleModel to 5e-5 (the reference's
+fp16 feature buffer) -- tests/test_reference_live_cpu.py.
 
 Everything is differentiable torch so autograd provides the backward oracle.
 ``bf16=True`` rounds at the same points as the CUDA kernels (tables, composed features,

@@ -338,3 +338,75 @@ def test_prune_and_render_glue_against_the_reference(ref):
     for cls in (vr.RenderOutput, OurRenderOutput):
         with pytest.raises(RuntimeError, match="Unknown data type"):
             cls.merge_render_outputs([cls(color=torch.rand(2, 3))])
+
+
+def test_scene_representation_glue_against_the_reference(ref):
+    """The reference's HumanRF.density / forward and Decomposition4D.forward (humanrf.py:158-208, decomposition4d.py:124-135)
+    executed live, with every tcnn module and the composition extension answering through the ORACLE's restatement of
+    that one module.  What is compared is therefore the glue the oracle restates around them: frame -> segment routing,
+    the +0.5 shift, local time, grid axis selection (xyz, xyt, yzt, xzt), composition call, truncated_exp * density_scale,
+    geometry-feature slicing, (d+1)/2, camera embeddings while training / zeros otherwise.  The reference stores the
+    composed features in fp16, hence the tolerances."""
+    from helpers import positions_of, synthetic_rays
+    from oracle import field as OF
+    from oracle import hashgrid
+
+    sizes, E = (6, 12, 6), 2
+    frames = tuple(range(15, 15 + sum(sizes)))
+    om = OF.make_model(sizes, frames, seed=5, table_init="trained", bf16=False, table_std=0.5, camera_embedding_dim=E)
+    try:
+        ref_model, _ = _import_reference_model()
+        from humanrf_b200.synthetic import MODEL_KW
+
+        theirs = ref_model.HumanRF(sorted_frame_numbers=frames, segment_sizes=sizes, **{**MODEL_KW, "camera_embedding_dim": E})
+    finally:
+        sys.modules.pop("tinycudann", None)
+    import humanrf.scene_representation.decomposition4d as d4
+
+    d4.Decomposition4D.to = lambda self, *a, **k: self                       # the reference parks idle segments on the CPU
+    d4.tensor_composition_native.compose_tensors_forward = \
+        lambda xyz, xyt, yzt, xzt, vectors, coords: OF.compose(xyz.float(), xyt.float(), yzt.float(), xzt.float(), vectors, coords).half()
+    for s, fg in enumerate(theirs.feature_grids):
+        with torch.no_grad():
+            fg.vectors.copy_(om.segments[s].vectors)
+        for k, name in enumerate(("xyz_encoding", "xyt_encoding", "yzt_encoding", "xzt_encoding")):
+            enc = getattr(fg, name)
+            enc.forward = (lambda x, s=s, k=k: hashgrid.encode(om.segments[s].grids[k], x.float(), om.segments[s].log2T).half())
+    theirs.sigma_net.forward = lambda f: torch.relu(f.float() @ om.w_sigma[0].t()) @ om.w_sigma[1].t()
+
+    def color_net(x):                                                        # [ (d+1)/2 | geo 15 | embedding E ] -> rgb
+        d, rest = x[:, :3].float() * 2 - 1, x[:, 3:].float()
+        inp = torch.cat((OF.sh4(d), rest, torch.ones((x.shape[0], 48 - 16 - rest.shape[1]))), dim=1)
+        w1, w2, w3 = om.w_color
+        h = torch.relu(torch.relu(inp @ w1.t()) @ w2.t())
+        return torch.sigmoid((h @ w3.t())[:, :3])
+
+    theirs.color_net.forward = color_net
+    with torch.no_grad():
+        theirs.camera_embeddings.weight.copy_(om.camera_embeddings)
+
+    b = synthetic_rays(96, 24, frames, ragged=True, seed=12, n_distinct_frames=len(frames))
+    pos, ri = positions_of(b), b["ri"]
+    dirs, fr, cams = b["d"][ri], b["frames"][ri].view(-1, 1), b["cams"][ri].view(-1, 1)
+    touched = set(om.f2s[b["frames"].numpy()].tolist())
+    assert len(touched) == 3                                                 # all three segments are exercised
+    for is_training in (True, False):
+        q = ref.qio.QueryInput(is_training=is_training, positions=pos, directions=dirs, frame_numbers=fr,
+                               unique_frame_numbers=torch.unique(b["frames"]).view(-1, 1), camera_numbers=cams)
+        with torch.no_grad():
+            out = theirs(q)
+            dens = theirs.density(q)
+            sigma, geo, rgb = om.forward(pos, dirs, fr.view(-1), cams.view(-1) if is_training else None)
+        assert out.density.shape == sigma.shape and out.geometry_features.shape == (pos.shape[0], 15) and out.radiance.shape == rgb.shape
+        assert torch.equal(out.density, dens.density)
+        rel = ((out.density - sigma).abs() / sigma.abs().clamp_min(1e-3)).max().item()
+        dg = (out.geometry_features.float() - geo).abs().max().item()
+        dc = (out.radiance - rgb).abs().max().item()
+        print(f"is_training={is_training}: density rel {rel:.2e}, geometry abs {dg:.2e}, radiance abs {dc:.2e}")
+        assert rel < 2e-3 and dg < 2e-3 and dc < 1e-3       # measured 5e-5 / 5e-5 / 5e-6 (the fp16 feature buffer)
+    # the embedding really is dropped at evaluation: the two passes differ in radiance only
+    q_eval = ref.qio.QueryInput(is_training=False, positions=pos, directions=dirs, frame_numbers=fr,
+                                unique_frame_numbers=torch.unique(b["frames"]).view(-1, 1), camera_numbers=cams)
+    q_train = dataclasses.replace(q_eval, is_training=True)
+    with torch.no_grad():
+        assert (theirs(q_eval).radiance - theirs(q_train).radiance).abs().max() > 1e-3
