@@ -144,8 +144,7 @@ def run_image(args, dev, rank, world):
     import numpy as np
     import torch.distributed as dist
 
-    sys.path.insert(0, str(ROOT / "tests"))
-    from scene import make_scene
+    from humanrf_b200.synthetic_scene import make_scene
 
     from humanrf_b200.dataset.occupancy_grid_native import OccupanyGrid
     from humanrf_b200.parallel import TileShardedRenderer

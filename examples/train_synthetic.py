@@ -27,7 +27,7 @@ from humanrf_b200.parallel import TileShardedRenderer  # noqa: E402
 from humanrf_b200.synthetic import make_model  # noqa: E402
 from humanrf_b200.training import FusedTrainer  # noqa: E402
 from humanrf_b200.volume_rendering import prune_samples  # noqa: E402
-from scene import SyntheticDataset  # noqa: E402
+from humanrf_b200.synthetic_scene import SyntheticDataset  # noqa: E402
 
 
 class TeacherDataset(SyntheticDataset):

@@ -72,8 +72,9 @@ __global__ void __launch_bounds__(256) visibility_kernel(const float* __restrict
 }
 
 // single-CTA exclusive scan of int32 counts -> offsets[n+1]; total also to counters[0]
-__global__ void __launch_bounds__(1024) scan_i32_kernel(const int32_t* __restrict__ in, int64_t n,
-                                                        int32_t* __restrict__ out, int64_t* __restrict__ counters) {
+// (`in` and `out` may be the same buffer -- hrf_prune scans its counts in place -- so neither is __restrict__)
+__global__ void __launch_bounds__(1024) scan_i32_kernel(const int32_t* in, int64_t n, int32_t* out,
+                                                        int64_t* __restrict__ counters) {
   __shared__ int warp_tot[32];
   __shared__ int carry;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;

@@ -130,6 +130,8 @@ __device__ __forceinline__ Cell to_cell(float scale, float v) {
   return c;
 }
 
+static __device__ __noinline__ uint32_t slow_mod(uint32_t v, uint32_t size) { return size != 0u ? v % size : 0u; }
+
 // Eight corner indices of one level (tcnn grid_index): dense x + y*res + z*res^2, or the
 // coherent prime hash, both reduced modulo the level's hashmap size.
 __device__ __forceinline__ void corner_indices(bool hashed, uint32_t res, uint32_t size, Cell a, Cell b, Cell c,
@@ -146,10 +148,14 @@ __device__ __forceinline__ void corner_indices(bool hashed, uint32_t res, uint32
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       uint32_t v = ((k & 1) ? a.g + 1u : a.g) + ((k & 2) ? b.g + 1u : b.g) * res + ((k & 4) ? c.g + 1u : c.g) * r2;
-      // v % size.  A dense level has res^3 <= size and v <= res^3 + res^2 + res < 2 size, so one subtraction settles it;
-      // the loop keeps the general meaning without inlining a 32-bit division at each of the 32 corners (that division
-      // was 654 of the forward kernel's 3 336 SASS instructions, and the kernel is instruction-cache sensitive).
-      while (v >= size && size != 0u) v -= size;   // (size == 0 only in a corrupt descriptor: do not spin on it)
+      // v % size.  A dense level has res^3 <= size and, for a position inside [0,1], v <= res^3 + res^2 + res < 2 size,
+      // so one subtraction settles it without inlining a 32-bit division at each of the 32 corners (that division was
+      // 654 of the forward kernel's 3 336 SASS instructions, and the kernel is instruction-cache sensitive).  Positions
+      // outside the unit cube (reachable through QueryInput) take the cold, out-of-line modulo: constant time, as tcnn.
+      if (v >= size) {
+        v -= size;
+        if (v >= size) v = slow_mod(v, size);
+      }
       idx[k] = v;
     }
   }

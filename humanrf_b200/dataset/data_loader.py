@@ -133,6 +133,7 @@ class DataLoader:
             self.cuda_grid_texture = occupancy_grid_native.OccupanyGrid(self.occupancy_grid_resolution,
                                                                         self.occupancy_grids_buffer_size)
         self.replacing = False
+        self.slot_pairs = [None] * self.buffer_size           # the (camera, frame) pair every pool slot currently holds
         self.camera_frame_pairs = self._camera_frame_pair_generator()
         for slot in range(self.buffer_size):
             self._load_and_copy_camera_frame_data(next(self.camera_frame_pairs), slot)
@@ -202,6 +203,7 @@ class DataLoader:
                 if self.mode == M.TRAINING:
                     self.frame_to_grid_texture[frame_number] = handle
             self.grid_texture_objects_cuda[buffer_index] = handle
+        self.slot_pairs[buffer_index] = (int(camera_number), int(frame_number))
         self.frame_numbers_cuda[buffer_index] = frame_number
         self.camera_numbers_cuda[buffer_index] = camera_number
         self.landscape_mode_cuda[buffer_index] = camera.width > camera.height
@@ -252,9 +254,12 @@ class DataLoader:
             ray_indices = torch.arange(start, end, dtype=torch.int64, device=self.device)
             image_num = self.iternum // self.num_pixels_per_camera
             slot = image_num % self.buffer_size
-            if start == 0 and image_num >= self.buffer_size:   # load the image on demand into its ring slot
-                self._load_and_copy_camera_frame_data(self.render_sequence[image_num % len(self.render_sequence)], slot)
             camera_number, frame_number = self.render_sequence[image_num]
+            # Load the image on demand into its ring slot whenever the slot holds another pair: the first pass beyond the
+            # pool size, and EVERY later pass (the reference's replacer thread keeps cycling through render_sequence,
+            # data_loader.py:471-506; the trainer re-iterates the validation loader every N steps).
+            if self.slot_pairs[slot] != (int(camera_number), int(frame_number)):
+                self._load_and_copy_camera_frame_data((camera_number, frame_number), slot)
             if not bool(self.landscape_mode_cuda[slot]):
                 height, width = self.resolution
             one = lambda t: t[slot:slot + 1]

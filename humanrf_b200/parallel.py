@@ -116,11 +116,17 @@ def allreduce_bucket_(flat: torch.Tensor, group=None, async_op: bool = False):
     return None if async_op else flat
 
 
-def broadcast_parameters_(params, src: int = 0, group=None) -> None:
-    """Make every replica start from rank `src`'s parameters."""
+def broadcast_parameters_(params, src: int = 0, group=None, model=None) -> None:
+    """Make every replica start from rank `src`'s parameters.  The parameter itself is broadcast into (under no_grad),
+    not `p.data`: an in-place write through `.data` does not bump `p._version`, and the native view decides from the
+    versions whether the bf16 shadow tables / the packed MLP blob have to be refreshed.  Pass `model` to also drop its
+    native view explicitly (for callers that wrote through raw pointers)."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        for p in params:
-            dist.broadcast(p.data, src=src, group=group)
+        with torch.no_grad():
+            for p in params:
+                dist.broadcast(p, src=src, group=group)
+    if model is not None and hasattr(model, "invalidate_native"):
+        model.invalidate_native()
 
 
 class TileShardedRenderer:

@@ -178,6 +178,12 @@ class HumanRF(torch.nn.Module):
         self._native.refresh()
         return self._native
 
+    def invalidate_native(self) -> None:
+        """Forces the next native() to re-cast every bf16 shadow table and repack the MLP blob.  refresh() follows the
+        parameters' autograd version counters; a write through `p.data` or a raw pointer does not move them."""
+        if self._native is not None:
+            self._native.versions = None
+
 
 class _NativeField:
     """Device-side view of a HumanRF module: bf16 shadow tables, packed MLP blob, descriptors."""

@@ -8,7 +8,7 @@ ROOT = Path(__file__).resolve().parent.parent
 if len(sys.argv) > 1:
     sys.path.insert(0, str(ROOT)); sys.path.insert(0, str(ROOT / "tests"))
     import torch
-    from scene import carve_scene
+    from humanrf_b200.synthetic_scene import carve_scene
 
     from humanrf_b200.toolbox import occupancy_grid_generation_native as ours
 

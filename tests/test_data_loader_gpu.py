@@ -76,3 +76,25 @@ def test_validation_covers_every_pixel_once_and_test_has_no_rgba(cuda):
         assert set(frames) == {15, 17}
     with pytest.raises(RuntimeError, match="render_sequence"):
         _loader(DL.Mode.TRAINING, max_num_frames_per_batch=2, use_mask=True, filter_light_bloom=False, render_sequence=seq)
+
+
+def test_validation_second_pass_reloads_the_ring(cuda):
+    """The trainer re-iterates the validation loader every N steps with max_buffer_size=1 (run.py): after a pass over a
+    render sequence longer than the pool, the slots hold the LAST images; the second pass must render the same images
+    as the first (colours, cameras, occupancy handles), not stale slots."""
+    from humanrf_b200.dataset.data_loader import DataLoader as DL
+
+    seq = [(0, 15), (3, 17), (1, 16)]
+    for max_buffer in (1, 2):
+        dl, ds, _ = _loader(DL.Mode.VALIDATION, render_sequence=seq, batch_size=64 * 48, max_buffer_size=max_buffer,
+                            use_mask=True, filter_light_bloom=False)
+        passes = []
+        for _ in range(2):
+            passes.append([(b.rgba.clone(), b.ray_origins.clone(), b.ray_directions.clone(), b.sample_distances.clone(),
+                            b.frame_numbers.clone(), b.camera_numbers.clone()) for b in dl])
+        assert len(passes[0]) == len(passes[1]) == 3
+        for first, second in zip(*passes):
+            for a, b in zip(first, second):
+                assert torch.equal(a, b)
+        # and the three images differ from each other (so a stale slot would have been noticed)
+        assert not torch.equal(passes[0][0][1][0], passes[0][1][1][0])
