@@ -232,7 +232,8 @@ def main():
                              sample_distances=tb["t"].view(-1, 1), ray_indices=tb["ri"]), model, None, is_training=False)
             w = out.weights_sum.clamp(min=1e-6)
             b["rgba"] = torch.cat((out.color / w, out.weights_sum), dim=1).clamp(0, 1).cpu()
-        trainer = FusedTrainer(model, lr=1e-2, world_size=world)
+        trainer = FusedTrainer(model, lr=1e-2, world_size=world, reuse=os.environ.get("HRF_TRAIN_REUSE", "feat"),
+                               exchange=os.environ.get("HRF_TRAIN_EXCHANGE", "p2p"))
     nat = model.native()
     g = {k: v.to(dev).contiguous() for k, v in b.items() if k in ("o", "d", "frames", "t", "ri", "rgba")}
     n = g["t"].shape[0]
@@ -373,6 +374,7 @@ def main():
             # re-read of tables / vectors 3072 B = 9216 B per sample.
             alg_per_sample, roof_kernel = 9216, "field_backward_kernel + grid_scatter_kernel"
             kern_ms = sum(a.elapsed_time(b) for a, b in bwd_ev[-args.steps:]) / args.steps
+            kept = [int(k) for k in kept]
             achieved = alg_per_sample * (sum(kept[-args.steps:]) / args.steps) / (kern_ms * 1e-3) / 1e9
         line = {
             "metric": METRIC[args.mode], "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,

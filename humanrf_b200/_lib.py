@@ -42,11 +42,31 @@ class Field(C.Structure):
 class Samples(C.Structure):
     _fields_ = [("positions", vp), ("directions", vp), ("frame_numbers", vp), ("ray_origins", vp),
                 ("ray_directions", vp), ("ray_frame_numbers", vp), ("sample_distances", vp), ("ray_indices", vp),
-                ("num_samples", i64), ("camera_numbers", vp), ("ray_camera_numbers", vp), ("use_camera_embeddings", i32)]
+                ("num_samples", i64), ("camera_numbers", vp), ("ray_camera_numbers", vp), ("use_camera_embeddings", i32),
+                ("num_samples_dev", vp)]
 
 
 class SegmentGrads(C.Structure):
     _fields_ = [("grid", vp * 4), ("vectors", vp)]
+
+
+class AdamTensor(C.Structure):
+    _fields_ = [("param", vp), ("exp_avg", vp), ("exp_avg_sq", vp), ("grad", vp), ("shadow_bf16", vp), ("blob_perm", vp),
+                ("active", vp), ("step", vp), ("n", i64), ("first_block", i64)]
+
+
+ADAM_BLOCK_ELEMS = 4096
+DP_MAX_WORLD = 8
+
+
+class DpPeers(C.Structure):
+    _fields_ = [("grad", vp * DP_MAX_WORLD), ("shadow", vp * DP_MAX_WORLD), ("world", i32), ("rank", i32)]
+
+
+class DpTensor(C.Structure):
+    _fields_ = [("param", vp), ("exp_avg", vp), ("exp_avg_sq", vp), ("grad_offset", i64), ("shadow_offset", i64),
+                ("local_shadow_bf16", vp), ("blob_perm", vp), ("active", vp), ("step", vp), ("n", i64),
+                ("shard_begin", i64), ("shard_end", i64), ("first_block", i64), ("sharded", i32)]
 
 
 _SIGNATURES = {
@@ -61,15 +81,24 @@ _SIGNATURES = {
     "hrf_sampler_workspace_bytes": (i64, [i64]),
     "hrf_sampler_samples": (C.c_int, [C.POINTER(SamplerParams), i64, vp, vp, vp, vp, vp, vp, vp, vp]),
     "hrf_field_forward": (C.c_int, [C.POINTER(Field), C.POINTER(Samples), C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),
+    "hrf_field_forward_from_features": (C.c_int, [C.POINTER(Field), C.POINTER(Samples), vp, vp, vp, vp, vp]),
     "hrf_density_early_stop_workspace_bytes": (i64, [i64]),
-    "hrf_field_density_early_stop": (C.c_int, [C.POINTER(Field), C.POINTER(Samples), vp, i64, f32, f32, vp, vp, vp]),
+    "hrf_field_density_early_stop": (C.c_int, [C.POINTER(Field), C.POINTER(Samples), vp, i64, f32, f32, vp, vp, vp, vp, vp]),
     "hrf_ray_offsets": (C.c_int, [vp, i64, i64, vp, vp]),
-    "hrf_prune": (C.c_int, [vp, vp, vp, vp, i64, f32, f32, f32, vp, vp, vp, vp, vp, vp]),
+    "hrf_prune": (C.c_int, [vp, vp, vp, vp, i64, f32, f32, f32, vp, vp, vp, vp, vp, vp, vp]),
     "hrf_composite_forward": (C.c_int, [vp, vp, vp, vp, i64, f32, vp, vp, vp, vp, vp]),
     "hrf_composite_backward": (C.c_int, [vp, vp, vp, vp, i64, f32, vp, vp, vp, vp, vp, vp]),
-    "hrf_field_backward": (C.c_int, [C.POINTER(Field), C.POINTER(Samples), vp, vp, vp, vp, vp, vp, vp, vp, vp]),
-    "hrf_field_backward_mlp": (C.c_int, [C.POINTER(Field), C.POINTER(Samples), vp, vp, vp, vp, vp, vp, vp]),
-    "hrf_field_backward_tables": (C.c_int, [C.POINTER(Field), C.POINTER(Samples), vp, vp, vp, C.c_int, C.c_int, vp]),
+    "hrf_field_backward": (C.c_int, [C.POINTER(Field), C.POINTER(Samples), vp, vp, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp]),
+    "hrf_field_backward_mlp": (C.c_int, [C.POINTER(Field), C.POINTER(Samples), vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "hrf_field_backward_tables": (C.c_int, [C.POINTER(Field), C.POINTER(Samples), vp, vp, vp, i64, vp, C.c_int, C.c_int, vp]),
+    "hrf_train_loss": (C.c_int, [vp, vp, vp, vp, i64, f32, f32, vp, vp, vp, vp, vp]),
+    "hrf_adam_multi": (C.c_int, [vp, C.c_int, i64, f32, f32, f32, f32, f32, C.c_int, vp]),
+    "hrf_peer_alloc": (C.c_int, [i64, C.POINTER(vp)]),
+    "hrf_peer_free": (C.c_int, [vp]),
+    "hrf_peer_export": (C.c_int, [vp, vp]),
+    "hrf_peer_open": (C.c_int, [vp, C.POINTER(vp)]),
+    "hrf_peer_close": (C.c_int, [vp]),
+    "hrf_dp_reduce_adam": (C.c_int, [C.POINTER(DpPeers), vp, C.c_int, i64, f32, f32, f32, f32, f32, vp]),
     "hrf_compose_tensors_forward": (C.c_int, [vp, vp, vp, vp, vp, vp, i64, C.c_int, C.c_int, vp, vp]),
     "hrf_compose_tensors_backward": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, i64, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),
     "hrf_adam_step": (C.c_int, [vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, C.c_int, f32, vp]),

@@ -119,7 +119,8 @@ __global__ void __launch_bounds__(256) prune_compact_kernel(const uint8_t* __res
                                                             const float* __restrict__ dist,
                                                             const int32_t* __restrict__ ray_off,
                                                             const int32_t* __restrict__ kept_off, int64_t num_rays,
-                                                            float* __restrict__ out_dist, int64_t* __restrict__ out_ri) {
+                                                            float* __restrict__ out_dist, int64_t* __restrict__ out_ri,
+                                                            int32_t* __restrict__ out_src) {
   const int lane = threadIdx.x & 31;
   const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (r >= num_rays) return;
@@ -133,6 +134,7 @@ __global__ void __launch_bounds__(256) prune_compact_kernel(const uint8_t* __res
       const int pos = base + __popc(m & ((1u << lane) - 1u));
       out_dist[pos] = dist[i];
       out_ri[pos] = r;
+      if (out_src != nullptr) out_src[pos] = i;
     }
     base += __popc(m);
   }
@@ -261,7 +263,7 @@ extern "C" int hrf_ray_offsets(const int64_t* ray_indices, int64_t num_samples, 
 extern "C" int hrf_prune(const float* sigma, const float* sample_distances, const int64_t* ray_indices,
                          const int32_t* ray_offsets, int64_t num_rays, float step, float early_stop_eps,
                          float alpha_thre, uint8_t* keep_mask, int32_t* kept_offsets, float* out_distances,
-                         int64_t* out_ray_indices, int64_t* counters, void* stream) {
+                         int64_t* out_ray_indices, int32_t* out_source_index, int64_t* counters, void* stream) {
   (void)ray_indices;
   HRF_REQUIRE(kept_offsets != nullptr && counters != nullptr, "null workspace");  // keep_mask may be NULL only for N == 0
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -277,7 +279,7 @@ extern "C" int hrf_prune(const float* sigma, const float* sample_distances, cons
   HRF_CHECK_LAUNCH();
   if (out_distances != nullptr) {
     prune_compact_kernel<<<warp_grid(num_rays), 256, 0, st>>>(keep_mask, sample_distances, ray_offsets, kept_offsets,
-                                                              num_rays, out_distances, out_ray_indices);
+                                                              num_rays, out_distances, out_ray_indices, out_source_index);
     HRF_CHECK_LAUNCH();
   }
   return 0;

@@ -47,7 +47,9 @@ struct BwdArgs {
   const hrf_segment_grads* seg_grads;
   const float* d_sigma;
   const float* d_rgb;
-  const uint4* feat_in;  // bf16 [N,32] saved by the forward, or NULL (re-encode)
+  const float* d_geo;    // [N,15] gradient of the geometry features, or NULL
+  const uint4* feat_in;  // bf16 [M,32] saved by a forward pass, or NULL (re-encode)
+  const int32_t* feat_index;  // row of feat_in per sample, or NULL (identity)
   float* d_mlp;
   float* d_emb;   // camera-embedding gradient [num_cameras, E] or NULL
   float2* dfeat;  // [16][N] float2 workspace: d(composed features)
@@ -169,7 +171,9 @@ struct ScatterArgs {
   const float2* dfeat;  // [16 levels][N] float2, written by field_backward_kernel
   const float4* pos4;   // [N] (x,y,z,t), written by field_backward_kernel
   const uint8_t* seg8;  // [N]
-  const uint32_t* egrid;  // bf16x2 [16*4][N] per-grid features saved by the forward, or NULL (re-gather the tables)
+  const uint32_t* egrid;  // bf16x2 [16*4][egrid_stride] per-grid features saved by a forward pass, or NULL (re-gather the tables)
+  const int32_t* feat_index;  // column of sample i inside egrid, or NULL (identity)
+  int64_t egrid_stride;
   int chunk;                   // consecutive samples per thread
   int tapstage;                // staged kernel: 1 = stage the interpolated vector values too (HRF_SCATTER_TAPSTAGE)
   int carry;                   // 1: carry the accumulators of corners shared with the previous cell (HRF_SCATTER_CARRY=0 disables)
@@ -178,7 +182,8 @@ struct ScatterArgs {
 
 __global__ void __launch_bounds__(256, 3) grid_scatter_kernel(const __grid_constant__ ScatterArgs a) {
   const hrf_field& f = a.f;
-  const int64_t n = a.s.num_samples;
+  const int64_t n = live_samples(a.s);
+  const int64_t ns = a.s.num_samples;   // row length of the level-major workspace
   const int kChunk = a.chunk;
   const int64_t i0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * kChunk;
   if (i0 >= n) return;
@@ -186,7 +191,7 @@ __global__ void __launch_bounds__(256, 3) grid_scatter_kernel(const __grid_const
   const int axis = (k == 0) ? 3 : (k == 1) ? 2 : (k == 2) ? 0 : 1;  // vector axis paired with grid k
   const float scale = f.level_scale[l];
   const uint32_t res = f.level_res[l];
-  const float2* __restrict__ dfl = a.dfeat + (size_t)l * n;
+  const float2* __restrict__ dfl = a.dfeat + (size_t)l * ns;
 
   // state of the current run
   const hrf_segment* cur_seg = nullptr;
@@ -272,7 +277,7 @@ __global__ void __launch_bounds__(256, 3) grid_scatter_kernel(const __grid_const
       accy[q] = __fmaf_rn(w[q], gy, accy[q]);
     }
     if (a.egrid != nullptr) {  // interpolated grid features saved by the forward
-      const uint32_t ev = __ldg(a.egrid + (size_t)(4 * l + k) * n + i);
+      const uint32_t ev = __ldg(a.egrid + (size_t)(4 * l + k) * a.egrid_stride + (a.feat_index != nullptr ? (int64_t)__ldg(a.feat_index + i) : i));
       ex = bf16_lo(ev), ey = bf16_hi(ev);
     } else {
 #pragma unroll
@@ -317,8 +322,10 @@ __global__ void __launch_bounds__(kStThreads, 6) grid_scatter_staged_kernel(cons
   extern __shared__ __align__(16) unsigned char staged_raw[];
   StagedSmem& sm = *reinterpret_cast<StagedSmem*>(staged_raw);
   const hrf_field& f = a.f;
-  const int64_t n = a.s.num_samples;
+  const int64_t n = live_samples(a.s);
+  const int64_t ns = a.s.num_samples;   // row length of the level-major workspace
   const int64_t base = (int64_t)blockIdx.x * kStSamples;
+  if (base >= n) return;
   const int tid = threadIdx.x;
   const int k = a.grid_first + (int)blockIdx.y % a.grid_count;
   const int l0 = ((int)blockIdx.y / a.grid_count) * kStLevels;
@@ -338,11 +345,16 @@ __global__ void __launch_bounds__(kStThreads, 6) grid_scatter_staged_kernel(cons
     const int l = l0 + li;
     __syncthreads();  // the previous level's readers are done with df / eg
     {
-      const float2* __restrict__ dfl = a.dfeat + (size_t)l * n + base;
+      const float2* __restrict__ dfl = a.dfeat + (size_t)l * ns + base;
       for (int s = tid; s < valid; s += kStThreads) sm.df[(s >> 3) * kStRow + (s & 7)] = __ldg(dfl + s);
       if (a.egrid != nullptr) {
-        const uint32_t* __restrict__ eg = a.egrid + (size_t)(4 * l + k) * n + base;
-        for (int s = tid; s < valid; s += kStThreads) sm.eg[(s >> 3) * kStRow + (s & 7)] = __ldg(eg + s);
+        const uint32_t* __restrict__ eg = a.egrid + (size_t)(4 * l + k) * a.egrid_stride;
+        if (a.feat_index == nullptr) {
+          for (int s = tid; s < valid; s += kStThreads) sm.eg[(s >> 3) * kStRow + (s & 7)] = __ldg(eg + base + s);
+        } else {   // survivors of a pruning pass: their columns in the candidates' buffer (mostly consecutive)
+          for (int s = tid; s < valid; s += kStThreads)
+            sm.eg[(s >> 3) * kStRow + (s & 7)] = __ldg(eg + __ldg(a.feat_index + base + s));
+        }
       }
       if (a.tapstage) {
         // the interpolated vector value of every sample, fetched here with 8 independent taps in flight per thread:
@@ -515,21 +527,23 @@ __global__ void __launch_bounds__(kTile, 2) field_backward_kernel(const __grid_c
   bool weights_ready = false, have_acc = false;
   uint32_t phase = 0;
 
-  const int64_t n = args.s.num_samples;
+  const int64_t n = live_samples(args.s);
+  const int64_t ns = args.s.num_samples;   // row length of the level-major workspace
   const int64_t num_tiles = (n + kTile - 1) / kTile;
   for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
     const int64_t i = tile * kTile + tid;
     const bool valid = i < n;
-    const Sample s = load_sample(f, args.s, i);
+    const Sample s = load_sample(f, args.s, i, n);
     if (valid) {
       args.pos4[i] = make_float4(s.x, s.y, s.z, s.t);
       args.seg8[i] = s.seg != nullptr ? (uint8_t)(s.seg - f.segments) : (uint8_t)255;
     }
     if (args.feat_in != nullptr) {
+      const int64_t row = !(valid && s.seg != nullptr) ? -1 : (args.feat_index != nullptr ? (int64_t)__ldg(args.feat_index + i) : i);
 #pragma unroll
       for (int kg = 0; kg < 4; ++kg)
         *reinterpret_cast<uint4*>(sm.feat + kg * kAChunk + roff) =
-            (valid && s.seg != nullptr) ? __ldg(args.feat_in + i * 4 + kg) : make_uint4(0, 0, 0, 0);
+            row >= 0 ? __ldg(args.feat_in + row * 4 + kg) : make_uint4(0, 0, 0, 0);
     } else {
       encode_to_smem<false, kLevelUnroll>(f, s, sm.feat, tid);
     }
@@ -545,7 +559,7 @@ __global__ void __launch_bounds__(kTile, 2) field_backward_kernel(const __grid_c
     mma_round(sm, phase, [&] { issue_layer(tm + kColWork, a_hs, wbase + kWSig2, 16, 64); });
     tmem_ld16(trow + kColWork, o);
     const float h0 = o[0];
-    const View vw = load_view(f, args.s, i);
+    const View vw = load_view(f, args.s, i, n);
     write_color_input(f, sm.cin, roff, vw, o);
     const int K1 = f.color_in_width;
     mma_round(sm, phase, [&] { issue_layer(tm + kColWork, a_cin, wbase + kWCol1, 64, K1); });
@@ -597,7 +611,12 @@ __global__ void __launch_bounds__(kTile, 2) field_backward_kernel(const __grid_c
         for (int e = 0; e < HRF_MAX_CAMERA_EMBEDDING_DIM; ++e)
           if (e < E) atomicAdd(args.d_emb + (size_t)vw.cam * E + e, dc[31 + e]);
       }
-      // d(sigma-net output): col 0 from the density (truncated_exp backward, activation.py:21), 1..15 = d geo
+      // d(sigma-net output): col 0 from the density (truncated_exp backward, activation.py:21), 1..15 = d geo: what the
+      // colour net sends back plus the caller's own gradient of QueryOutput.geometry_features (humanrf.py:185-186)
+      if (args.d_geo != nullptr && valid) {
+#pragma unroll
+        for (int j = 0; j < HRF_GEO_DIM; ++j) dc[16 + j] += __ldg(args.d_geo + i * HRF_GEO_DIM + j);
+      }
       float dh0 = 0.f;
       if (valid && args.d_sigma != nullptr)
         dh0 = args.d_sigma[i] * f.density_scale * __expf(fminf(fmaxf(h0, -15.f), 15.f));
@@ -623,7 +642,7 @@ __global__ void __launch_bounds__(kTile, 2) field_backward_kernel(const __grid_c
       tmem_ld32(trow + kColWork, df);
       if (valid) {
 #pragma unroll
-        for (int l = 0; l < 16; ++l) args.dfeat[(size_t)l * n + i] = make_float2(df[2 * l], df[2 * l + 1]);
+        for (int l = 0; l < 16; ++l) args.dfeat[(size_t)l * ns + i] = make_float2(df[2 * l], df[2 * l + 1]);
       }
     }
   }
@@ -668,13 +687,13 @@ __global__ void __launch_bounds__(kTile, 2) field_backward_kernel(const __grid_c
 using namespace hrf;
 
 extern "C" int hrf_field_backward_mlp(const hrf_field* f, const hrf_samples* s, const float* d_sigma, const float* d_rgb,
-                                      const void* feat_bf16, float* d_mlp, float* d_camera_embeddings, void* workspace,
-                                      void* stream) {
+                                      const float* d_geo, const void* feat_bf16, const int32_t* feat_index, float* d_mlp,
+                                      float* d_camera_embeddings, void* workspace, void* stream) {
   HRF_REQUIRE(f != nullptr && s != nullptr, "null argument");
   HRF_REQUIRE(f->num_segments < 255, "at most 254 temporal segments");
   if (s->num_samples == 0) return 0;
   HRF_REQUIRE(workspace != nullptr, "hrf_field_backward needs a workspace of 160 bytes per sample");
-  HRF_REQUIRE(d_sigma != nullptr || d_rgb != nullptr, "no upstream gradient given");
+  HRF_REQUIRE(d_sigma != nullptr || d_rgb != nullptr || d_geo != nullptr, "no upstream gradient given");
   if (s->ray_origins == nullptr) {
     HRF_REQUIRE(s->positions && s->frame_numbers, "query form needs positions and frame numbers");
     HRF_REQUIRE(d_rgb == nullptr || s->directions, "radiance gradients need directions");
@@ -685,7 +704,9 @@ extern "C" int hrf_field_backward_mlp(const hrf_field* f, const hrf_samples* s, 
   a.seg_grads = nullptr;
   a.d_sigma = d_sigma;
   a.d_rgb = d_rgb;
+  a.d_geo = d_geo;
   a.feat_in = reinterpret_cast<const uint4*>(feat_bf16);
+  a.feat_index = feat_bf16 != nullptr ? feat_index : nullptr;
   a.d_mlp = d_mlp;
   a.d_emb = d_camera_embeddings;
   a.dfeat = reinterpret_cast<float2*>(workspace);
@@ -709,8 +730,8 @@ extern "C" int hrf_field_backward_mlp(const hrf_field* f, const hrf_samples* s, 
 }
 
 extern "C" int hrf_field_backward_tables(const hrf_field* f, const hrf_samples* s, const hrf_segment_grads* seg_grads,
-                                         const void* grid_feat_bf16, const void* workspace, int grid_first, int grid_count,
-                                         void* stream) {
+                                         const void* grid_feat_bf16, const int32_t* feat_index, int64_t grid_feat_stride,
+                                         const void* workspace, int grid_first, int grid_count, void* stream) {
   HRF_REQUIRE(f != nullptr && s != nullptr && seg_grads != nullptr, "null argument");
   HRF_REQUIRE(grid_first >= 0 && grid_count >= 1 && grid_first + grid_count <= 4, "grids are 0..3 (xyz, xyt, yzt, xzt)");
   if (s->num_samples == 0) return 0;
@@ -723,6 +744,8 @@ extern "C" int hrf_field_backward_tables(const hrf_field* f, const hrf_samples* 
   sa.pos4 = reinterpret_cast<const float4*>(reinterpret_cast<const char*>(workspace) + 128 * (size_t)s->num_samples);
   sa.seg8 = reinterpret_cast<const uint8_t*>(reinterpret_cast<const char*>(workspace) + 144 * (size_t)s->num_samples);
   sa.egrid = reinterpret_cast<const uint32_t*>(grid_feat_bf16);
+  sa.feat_index = grid_feat_bf16 != nullptr ? feat_index : nullptr;
+  sa.egrid_stride = grid_feat_stride > 0 ? grid_feat_stride : s->num_samples;
   sa.grid_first = grid_first;
   sa.grid_count = grid_count;
   const int kChunk = [] { const char* e = getenv("HRF_SCATTER_CHUNK"); const int v = e ? atoi(e) : 0; return v > 0 ? v : kChunkDefault; }();
@@ -745,10 +768,12 @@ extern "C" int hrf_field_backward_tables(const hrf_field* f, const hrf_samples* 
 }
 
 extern "C" int hrf_field_backward(const hrf_field* f, const hrf_samples* s, const hrf_segment_grads* seg_grads,
-                                  const float* d_sigma, const float* d_rgb, const void* feat_bf16,
-                                  const void* grid_feat_bf16, float* d_mlp, float* d_camera_embeddings, void* workspace,
-                                  void* stream) {
+                                  const float* d_sigma, const float* d_rgb, const float* d_geo, const void* feat_bf16,
+                                  const void* grid_feat_bf16, const int32_t* feat_index, int64_t grid_feat_stride,
+                                  float* d_mlp, float* d_camera_embeddings, void* workspace, void* stream) {
   HRF_REQUIRE(seg_grads != nullptr, "null argument");
-  if (int rc = hrf_field_backward_mlp(f, s, d_sigma, d_rgb, feat_bf16, d_mlp, d_camera_embeddings, workspace, stream)) return rc;
-  return hrf_field_backward_tables(f, s, seg_grads, grid_feat_bf16, workspace, 0, 4, stream);
+  if (int rc = hrf_field_backward_mlp(f, s, d_sigma, d_rgb, d_geo, feat_bf16, feat_index, d_mlp, d_camera_embeddings, workspace,
+                                      stream))
+    return rc;
+  return hrf_field_backward_tables(f, s, seg_grads, grid_feat_bf16, feat_index, grid_feat_stride, workspace, 0, 4, stream);
 }

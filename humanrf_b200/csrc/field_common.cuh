@@ -50,8 +50,17 @@ struct FieldArgs {
   float* rgb;
   uint4* feat;     // bf16 [N,32] composed features (optional output)
   uint32_t* egrid; // bf16x2 [16*4][N] per-grid interpolated features (optional output, for the backward scatter)
+  const uint4* feat_in;       // bf16 [M,32] composed features of an earlier pass (kFromFeat kernels: no encode)
+  const int32_t* feat_index;  // row of feat_in per sample, or NULL (identity)
   int mode;
 };
+
+// Live number of samples: the device scalar of a sync-free pipeline (bounded by the capacity), or the host value.
+__device__ __forceinline__ int64_t live_samples(const hrf_samples& s) {
+  if (s.num_samples_dev == nullptr) return s.num_samples;
+  const int64_t n = *reinterpret_cast<const volatile int64_t*>(s.num_samples_dev);
+  return n < s.num_samples ? (n < 0 ? 0 : n) : s.num_samples;
+}
 
 struct Sample {
   float x, y, z, t;        // normalised coordinates in [0,1] (positions + 0.5, local time)
@@ -64,11 +73,11 @@ struct View {
   int cam;                 // camera row of the embedding table, or -1 (zeros: evaluation / no embedding)
 };
 
-__device__ __forceinline__ Sample load_sample(const hrf_field& f, const hrf_samples& s, int64_t i) {
+__device__ __forceinline__ Sample load_sample(const hrf_field& f, const hrf_samples& s, int64_t i, int64_t n_live) {
   Sample o;
   o.seg = nullptr;
   o.x = o.y = o.z = o.t = 0.f;
-  if (i >= s.num_samples) return o;
+  if (i >= n_live) return o;
   int frame;
   float px, py, pz;
   if (s.ray_origins != nullptr) {
@@ -96,11 +105,11 @@ __device__ __forceinline__ Sample load_sample(const hrf_field& f, const hrf_samp
   return o;
 }
 
-__device__ __forceinline__ View load_view(const hrf_field& f, const hrf_samples& s, int64_t i) {
+__device__ __forceinline__ View load_view(const hrf_field& f, const hrf_samples& s, int64_t i, int64_t n_live) {
   View v;
   v.dx = v.dy = v.dz = 0.f;
   v.cam = -1;
-  if (i >= s.num_samples) return v;
+  if (i >= n_live) return v;
   const bool want_cam = s.use_camera_embeddings && f.camera_embeddings != nullptr;
   if (s.ray_origins != nullptr) {
     const int64_t r = __ldg(s.ray_indices + i);

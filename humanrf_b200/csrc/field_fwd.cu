@@ -101,7 +101,9 @@ __device__ __forceinline__ void store_hidden(unsigned char* hbuf, int row, const
   }
 }
 
-template <bool kSimt, int kCtasPerSm, bool kSaveGrid = false, int kLevelUnroll = 4>
+// kFromFeat: the composed features come from an earlier pass (args.feat_in, optionally through args.feat_index) and the
+// encode is skipped: the MLP half of the kernel alone (render pass of the survivors of prune_samples).
+template <bool kSimt, int kCtasPerSm, bool kSaveGrid = false, int kLevelUnroll = 4, bool kFromFeat = false>
 __global__ void __launch_bounds__(kTile, kCtasPerSm) field_forward_kernel(const __grid_constant__ FieldArgs args) {
   extern __shared__ unsigned char smem_raw[];
   FwdSmem& sm = *reinterpret_cast<FwdSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
@@ -130,7 +132,8 @@ __global__ void __launch_bounds__(kTile, kCtasPerSm) field_forward_kernel(const 
   bool weights_ready = false;
   uint32_t phase = 0;
 
-  const int64_t n = args.s.num_samples;
+  const int64_t n = live_samples(args.s);
+  const int64_t n_stride = args.s.num_samples;   // row length of the level-major [64][N] output
   const int64_t num_tiles = (n + kTile - 1) / kTile;
   // Early-stop schedule (density-only pass of prune_samples, volume_rendering.py:66-84).  Work items are
   // (chunk k, ray r) = samples [off[r]+128k, off[r]+128(k+1)) of ray r, pulled from a global counter in the order
@@ -181,9 +184,17 @@ __global__ void __launch_bounds__(kTile, kCtasPerSm) field_forward_kernel(const 
         continue;
       }
     }
-    const Sample s = load_sample(f, args.s, valid ? i : n);
-    encode_to_smem<kSaveGrid, kLevelUnroll>(f, s, sm.a, tid, (kSaveGrid && valid && s.seg != nullptr) ? args.egrid : nullptr, i, n);
-    if (args.feat != nullptr && valid) {
+    if constexpr (kFromFeat) {
+      const uint32_t ro = a_row_off(tid);
+      const int64_t row = !valid ? -1 : (args.feat_index != nullptr ? (int64_t)__ldg(args.feat_index + i) : i);
+#pragma unroll
+      for (int kg = 0; kg < 4; ++kg)
+        *reinterpret_cast<uint4*>(sm.a + kg * kAChunk + ro) = row >= 0 ? __ldg(args.feat_in + row * 4 + kg) : make_uint4(0, 0, 0, 0);
+    } else {
+      const Sample s = load_sample(f, args.s, valid ? i : n, n);
+      encode_to_smem<kSaveGrid, kLevelUnroll>(f, s, sm.a, tid, (kSaveGrid && valid && s.seg != nullptr) ? args.egrid : nullptr, i, n_stride);
+    }
+    if (!kFromFeat && args.feat != nullptr && valid) {
       const uint32_t ro = a_row_off(tid);
 #pragma unroll
       for (int kg = 0; kg < 4; ++kg) args.feat[i * 4 + kg] = *reinterpret_cast<const uint4*>(sm.a + kg * kAChunk + ro);
@@ -218,7 +229,7 @@ __global__ void __launch_bounds__(kTile, kCtasPerSm) field_forward_kernel(const 
     if (args.mode == 0) continue;
 
     // ---- colour net: [SH16 | geo15 | 1.0] -> 64 (ReLU) -> 64 (ReLU) -> 16 -> sigmoid[:3] ----
-    write_color_input(f, sm.a, a_row_off(tid), load_view(f, args.s, valid ? i : n), o);
+    write_color_input(f, sm.a, a_row_off(tid), load_view(f, args.s, valid ? i : n, n), o);
     if (f.color_in_width == 48) run_layer<kSimt, 64, 48>(sm, sm.a, kWCol1, phase, v);
     else run_layer<kSimt, 64, 32>(sm, sm.a, kWCol1, phase, v);
     store_hidden(sm.a, tid, v);
@@ -272,7 +283,8 @@ static int launch_field_forward(const FieldArgs& a, int mlp_impl, cudaStream_t s
   // the limiter.  Default 1.
   static const int unroll = [] { const char* e = getenv("HRF_FWD_UNROLL"); const int v = e ? atoi(e) : 1; return (v == 2 || v == 4) ? v : 1; }();
   int rc;
-  if (mlp_impl != 0) rc = launch(field_forward_kernel<true, 4>);
+  if (a.feat_in != nullptr) rc = launch(field_forward_kernel<false, 5, false, 1, true>);
+  else if (mlp_impl != 0) rc = launch(field_forward_kernel<true, 4>);
   else if (a.egrid != nullptr && unroll == 2) rc = launch(field_forward_kernel<false, 5, true, 2>);
   else if (a.egrid != nullptr && unroll == 1) rc = launch(field_forward_kernel<false, 5, true, 1>);
   else if (a.egrid != nullptr) rc = launch(field_forward_kernel<false, 5, true>);   // training forward: also saves e_k
@@ -319,8 +331,31 @@ extern "C" int hrf_field_forward(const hrf_field* f, const hrf_samples* s, int m
   a.rgb = rgb;
   a.feat = reinterpret_cast<uint4*>(feat_bf16);
   a.egrid = reinterpret_cast<uint32_t*>(grid_feat_bf16);
+  a.feat_in = nullptr;
+  a.feat_index = nullptr;
   a.mode = mode;
   return launch_field_forward(a, mlp_impl, reinterpret_cast<cudaStream_t>(stream), false);
+}
+
+extern "C" int hrf_field_forward_from_features(const hrf_field* f, const hrf_samples* s, const void* feat_in_bf16,
+                                               const int32_t* feat_index, float* sigma, float* rgb, void* stream) {
+  if (int rc = check_field_args(f, s, 1)) return rc;
+  HRF_REQUIRE(feat_in_bf16 != nullptr, "null feature buffer");
+  HRF_REQUIRE(s->ray_origins != nullptr, "hrf_field_forward_from_features needs the ray-batch form");
+  if (s->num_samples == 0) return 0;
+  FieldArgs a;
+  a.f = *f;
+  a.s = *s;
+  a.es = EarlyStop{};
+  a.sigma = sigma;
+  a.geo = nullptr;
+  a.rgb = rgb;
+  a.feat = nullptr;
+  a.egrid = nullptr;
+  a.feat_in = reinterpret_cast<const uint4*>(feat_in_bf16);
+  a.feat_index = feat_index;
+  a.mode = 1;
+  return launch_field_forward(a, 0, reinterpret_cast<cudaStream_t>(stream), s->num_samples_dev != nullptr);
 }
 
 namespace hrf {
@@ -338,7 +373,7 @@ extern "C" int64_t hrf_density_early_stop_workspace_bytes(int64_t num_rays) { re
 
 extern "C" int hrf_field_density_early_stop(const hrf_field* f, const hrf_samples* s, const int32_t* ray_offsets,
                                             int64_t num_rays, float step, float stop_depth, float* sigma,
-                                            void* workspace, void* stream) {
+                                            void* feat_bf16, void* grid_feat_bf16, void* workspace, void* stream) {
   if (int rc = check_field_args(f, s, 0)) return rc;
   HRF_REQUIRE(s->ray_origins != nullptr, "the early-stop density pass needs the ray-batch form");
   HRF_REQUIRE(ray_offsets != nullptr && sigma != nullptr && workspace != nullptr, "null argument");
@@ -360,8 +395,10 @@ extern "C" int hrf_field_density_early_stop(const hrf_field* f, const hrf_sample
   a.sigma = sigma;
   a.geo = nullptr;
   a.rgb = nullptr;
-  a.feat = nullptr;
-  a.egrid = nullptr;
+  a.feat = reinterpret_cast<uint4*>(feat_bf16);
+  a.egrid = reinterpret_cast<uint32_t*>(grid_feat_bf16);
+  a.feat_in = nullptr;
+  a.feat_index = nullptr;
   a.mode = 0;
   ray_max_chunks_kernel<<<(unsigned)((num_rays + 255) / 256), 256, 0, st>>>(ray_offsets, num_rays,
                                                                            reinterpret_cast<int32_t*>(ws + 16));

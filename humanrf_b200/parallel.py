@@ -25,6 +25,16 @@ def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
     return start, start + base + (1 if rank < rem else 0)
 
 
+def shard_bounds(n: int, rank: int, world: int, align: int = 4096) -> Tuple[int, int]:
+    """[begin, end) of rank's slice of an n-element tensor under data-parallel sharding of the optimiser
+    (FusedTrainer exchange="p2p"): equal slices rounded up to `align` elements (the Adam kernel's block), the last
+    ranks' slices may be short or empty.  Every element belongs to exactly one rank."""
+    per = -(-n // world)
+    per = -(-per // align) * align
+    begin = min(rank * per, n)
+    return begin, min(begin + per, n)
+
+
 def deal_round_robin(items: Sequence, rank: int, world: int) -> List:
     """(camera, frame) pairs of a render sequence dealt round-robin to ranks."""
     return [x for i, x in enumerate(items) if i % world == rank]

@@ -272,6 +272,20 @@ class _NativeField:
                     self.repack_mlp()
             self.versions = versions
 
+    def adopt_shadows(self, views: List[List[torch.Tensor]]) -> None:
+        """Re-point the bf16 shadow tables at caller-provided storage (views[s][k], already holding the current values):
+        the data-parallel trainer keeps them in one peer-visible buffer that the owners of the slices write remotely."""
+        m = self.model
+        segs = (L.Segment * m.num_segments)()
+        raw = self.seg_dev.cpu().numpy().tobytes()
+        C.memmove(segs, raw, len(raw))
+        for s in range(m.num_segments):
+            for k in range(4):
+                assert views[s][k].numel() == self.shadows[s][k].numel() and views[s][k].dtype == torch.bfloat16
+                segs[s].grid[k] = views[s][k].data_ptr()
+        self.shadows = views
+        self.seg_dev.copy_(torch.from_numpy(np.frombuffer(bytes(segs), dtype=np.uint8).copy()))
+
     @property
     def n_table_params(self) -> int:
         return 5 * self.model.num_segments
@@ -299,7 +313,9 @@ class _NativeField:
         return s
 
     def samples_rays(self, ray_origins, ray_directions, ray_frames, distances, ray_indices,
-                     ray_cameras=None) -> L.Samples:
+                     ray_cameras=None, count_dev: Optional[torch.Tensor] = None) -> L.Samples:
+        """`count_dev` (int64 device scalar): the live number of samples; distances / ray_indices are then capacity-sized
+        buffers and nothing has to be read back to launch the kernels (hrf_samples.num_samples_dev)."""
         s = L.Samples()
         s.ray_origins = ray_origins.data_ptr()
         s.ray_directions = ray_directions.data_ptr()
@@ -310,7 +326,9 @@ class _NativeField:
         if ray_cameras is not None:
             s.ray_camera_numbers = ray_cameras.data_ptr()
             s.use_camera_embeddings = 1
-        s._keep = (ray_origins, ray_directions, ray_frames, distances, ray_indices, ray_cameras)
+        if count_dev is not None:
+            s.num_samples_dev = count_dev.data_ptr()
+        s._keep = (ray_origins, ray_directions, ray_frames, distances, ray_indices, ray_cameras, count_dev)
         return s
 
     def forward(self, samples: L.Samples, mode: int, want_geo: bool, want_feat: bool, mlp_impl: int = 0):
@@ -332,22 +350,41 @@ class _NativeField:
     def saved_features(saved: torch.Tensor, n: int) -> torch.Tensor:
         return saved[: n * 32].view(n, 32)
 
-    def density_early_stop(self, samples: L.Samples, ray_offsets: torch.Tensor, num_rays: int, step: float,
-                           stop_depth: float = 9.4) -> torch.Tensor:
-        """Density-only pass for prune_samples with the exact early stop (hrf_field_density_early_stop)."""
+    def forward_from_features(self, samples: L.Samples, feat_in: torch.Tensor, feat_index: Optional[torch.Tensor],
+                              sigma: Optional[torch.Tensor] = None, rgb: Optional[torch.Tensor] = None):
+        """Sigma / colour MLPs on composed features an earlier pass wrote (`feat_in` bf16 [M,32], row `feat_index[i]`
+        for sample i): the render pass of the survivors of prune_samples without a second encode."""
         dev = self._device()
         n = int(samples.num_samples)
-        sigma = torch.empty(n, dtype=torch.float32, device=dev)
+        sigma = torch.empty(n, dtype=torch.float32, device=dev) if sigma is None else sigma
+        rgb = torch.empty((n, 3), dtype=torch.float32, device=dev) if rgb is None else rgb
+        L.check(L.lib().hrf_field_forward_from_features(C.byref(self.field), C.byref(samples), feat_in.data_ptr(),
+                                                        L.ptr(feat_index), sigma.data_ptr(), rgb.data_ptr(), L.stream()))
+        return sigma, rgb
+
+    def density_early_stop(self, samples: L.Samples, ray_offsets: torch.Tensor, num_rays: int, step: float,
+                           stop_depth: float = 9.4, save: str = "none", sigma: Optional[torch.Tensor] = None,
+                           saved: Optional[torch.Tensor] = None):
+        """Density-only pass for prune_samples with the exact early stop (hrf_field_density_early_stop).
+        save = "none" -> sigma; "feat" -> (sigma, saved) with the composed features [N,32] bf16 of every evaluated sample;
+        "feat+grid" -> the same buffer followed by the per-(level, grid) features [64][N] (layout of forward())."""
+        dev = self._device()
+        n = int(samples.num_samples)
+        sigma = torch.empty(n, dtype=torch.float32, device=dev) if sigma is None else sigma
         lib = L.lib()
         ws = torch.empty(int(lib.hrf_density_early_stop_workspace_bytes(num_rays)), dtype=torch.uint8, device=dev)
+        if save != "none" and saved is None:
+            saved = torch.empty(n * (160 if save == "feat+grid" else 32), dtype=torch.bfloat16, device=dev)
+        egrid = saved.data_ptr() + 64 * n if (save == "feat+grid" and n > 0) else None
         L.check(lib.hrf_field_density_early_stop(C.byref(self.field), C.byref(samples), ray_offsets.data_ptr(), num_rays,
-                                                 float(step), float(stop_depth), sigma.data_ptr(), ws.data_ptr(),
-                                                 L.stream()))
-        return sigma
+                                                 float(step), float(stop_depth), sigma.data_ptr(),
+                                                 L.ptr(saved) if save != "none" else None, egrid, ws.data_ptr(), L.stream()))
+        return sigma if save == "none" else (sigma, saved)
 
-    def backward(self, samples: L.Samples, d_sigma, d_rgb, feat, grad_tensors: List[torch.Tensor], per_table: bool = False):
+    def backward(self, samples: L.Samples, d_sigma, d_rgb, feat, grad_tensors: List[torch.Tensor], per_table: bool = False,
+                 d_geo=None):
         """grad_tensors: fp32 buffers in hot_parameters() order (accumulated into).  per_table launches the scatter once
-        per grid (the schedule the data-parallel trainer overlaps with its all-reduces) instead of once for all four."""
+        per grid instead of once for all four.  d_geo: fp32 [N,15] gradient of the geometry features, or None."""
         m = self.model
         dev = self._device()
         sg = (L.SegmentGrads * m.num_segments)()
@@ -366,14 +403,15 @@ class _NativeField:
         egrid = feat.data_ptr() + 64 * n if (feat is not None and feat.numel() >= n * 160 and n > 0) else None
         if per_table:
             L.check(L.lib().hrf_field_backward_mlp(C.byref(self.field), C.byref(samples), L.ptr(d_sigma), L.ptr(d_rgb),
-                                                   L.ptr(feat), d_mlp.data_ptr(), L.ptr(d_emb), ws.data_ptr(), L.stream()))
+                                                   L.ptr(d_geo), L.ptr(feat), None, d_mlp.data_ptr(), L.ptr(d_emb),
+                                                   ws.data_ptr(), L.stream()))
             for k in range(4):
                 L.check(L.lib().hrf_field_backward_tables(C.byref(self.field), C.byref(samples), sg_dev.data_ptr(), egrid,
-                                                          ws.data_ptr(), k, 1, L.stream()))
+                                                          None, 0, ws.data_ptr(), k, 1, L.stream()))
         else:
             L.check(L.lib().hrf_field_backward(C.byref(self.field), C.byref(samples), sg_dev.data_ptr(), L.ptr(d_sigma),
-                                               L.ptr(d_rgb), L.ptr(feat), egrid, d_mlp.data_ptr(), L.ptr(d_emb),
-                                               ws.data_ptr(), L.stream()))
+                                               L.ptr(d_rgb), L.ptr(d_geo), L.ptr(feat), egrid, None, 0, d_mlp.data_ptr(),
+                                               L.ptr(d_emb), ws.data_ptr(), L.stream()))
         grad_tensors[i].add_(d_mlp[:MLP_SIGMA_PARAMS])
         grad_tensors[i + 1].add_(d_mlp[MLP_SIGMA_PARAMS:])
         return sg_dev  # keep alive until the kernel has run (stream-ordered free is safe, but be explicit)
@@ -401,11 +439,11 @@ class _FieldFunction(torch.autograd.Function):
         samples = nat.samples_query(pos, dirs, frames, cams)
         sigma, geo, rgb, feat = nat.forward(samples, mode, want_geo=True, want_feat=needs_grad)
         ctx.model, ctx.mode, ctx.active = model, mode, active
+        ctx.set_materialize_grads(False)    # outputs the caller does not use arrive as None in backward, not as zero tensors
         ctx.save_for_backward(pos, dirs if dirs is not None else pos, frames, feat if feat is not None else pos,
                               cams if cams is not None else frames)
         ctx.has_dirs, ctx.has_cams = dirs is not None, cams is not None
-        geo_out = geo[:, 1:]
-        ctx.mark_non_differentiable(geo_out)
+        geo_out = geo[:, 1:]            # differentiable: humanrf.py:185-186 hands sigma_net's outputs 1..15 to the caller
         if rgb is None:
             rgb = sigma.new_zeros((0, 3))
             ctx.mark_non_differentiable(rgb)
@@ -423,7 +461,8 @@ class _FieldFunction(torch.autograd.Function):
         dr = None if (d_rgb is None or ctx.mode == 0) else _as_f32c(d_rgb)
         if ds is None:
             ds = torch.zeros(pos.shape[0], dtype=torch.float32, device=pos.device)
-        keep = nat.backward(samples, ds, dr, feat, grads)
+        dg = None if d_geo is None else _as_f32c(d_geo)
+        keep = nat.backward(samples, ds, dr, feat, grads, d_geo=dg)
         del keep
         if ctx.active is not None:      # segments the batch did not touch get no gradient at all (None), as in the reference
             from ..parallel import mask_inactive_segment_grads

@@ -1,13 +1,25 @@
-"""Native training step for the HumanRF hot path (the fast path behind bench.py --mode train and the
-data-parallel driver).  Same maths as the reference's Trainer.train_step (humanrf/trainer.py:229-255:
-random background, Huber(delta=0.01) + 1e-3 * BCE, Adam lr 1e-2 betas (0.9,0.99) eps 1e-15,
-lr * lr_decay^(min(step/max,1)), run.py:101-104), but:
+"""Native training step for the HumanRF hot path (the fast path behind bench.py and the data-parallel driver).
+Same maths as the reference's Trainer.train_step (humanrf/trainer.py:229-255: random background,
+Huber(delta=0.01) + 1e-3 * BCE, Adam lr 1e-2 betas (0.9,0.99) eps 1e-15, lr * lr_decay^(min(step/max,1)),
+run.py:101-104), but built so that ONE step never stops the device:
 
-* gradients are written by the fused backward kernels straight into ONE flat fp32 bucket (no per-parameter
-  zero-filled tensors, no autograd graph), laid out grid-major so that under data parallelism the bucket
-  is reduced in 5 NCCL messages, each overlapping the scatter of the next table and the Adam of the previous one;
-* Adam is one fused kernel per parameter that also refreshes the bf16 shadow table the forward reads;
+* prune_samples' density pass keeps the composed features of every candidate (64 B/sample); the render pass of the
+  survivors runs the two MLPs on those features instead of encoding the survivors a second time
+  (`reuse="feat"`; "feat+grid" also keeps the per-grid features for the scatter, "none" is the round-1 flow);
+* the survivor count stays on the device (hrf_samples.num_samples_dev): no `.item()` between pruning and the forward;
+* loss forward + backward is one kernel (hrf_train_loss), Adam over all tensors is one launch (hrf_adam_multi) with
+  device-side step counters / active-segment flags, it refreshes the bf16 shadow tables and the packed MLP blob and
+  leaves the gradient bucket zeroed for the next step;
+* gradients go straight into ONE flat fp32 bucket (no per-parameter zero-filled tensors, no autograd graph);
 * bf16 needs no GradScaler, so the inf-check host sync of trainer.py:250-252 disappears.
+
+Data parallel, one process per GPU, `exchange=`:
+  "p2p"  (default) the bucket and the shadow tables live in peer-visible memory; after the backward ONE kernel
+         (hrf_dp_reduce_adam) does reduce-scatter + rank-sharded Adam + all-gather of the bf16 shadows over NVLink peer
+         memory, bracketed by two tiny NCCL all-reduces that act as barriers (the first also carries the
+         active-segment flags).  fp32 masters and moments of the hash tables are sharded 1/world per rank
+         (`gather_master_parameters()` re-assembles them for checkpoints);
+  "nccl" one all-reduce of the bucket, then the single-GPU Adam on every rank.
 
 The autograd-compatible route (humanrf_b200.volume_rendering.render + torch.optim.Adam) stays available for
 running the reference's trainer.py unchanged.
@@ -22,51 +34,194 @@ import torch
 import torch.distributed as dist
 
 from . import _lib as L
-from .parallel import (active_segments, allreduce_bucket_, allreduce_spans, grid_major_bucket_layout,
-                       union_batch_loss_scale)
+from .parallel import active_segments, grid_major_bucket_layout, shard_bounds, union_batch_loss_scale
+from .scene_representation.grid_layout import MLP_SIGMA_PARAMS, mlp_blob_permutation
 from .scene_representation.humanrf import HumanRF
 from .volume_rendering import ray_offsets
+
+
+class _RawCuda:
+    """__cuda_array_interface__ view of device memory the C library allocated (peer-visible buffers)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def _device_struct_array(items, dev) -> torch.Tensor:
+    raw = b"".join(bytes(x) for x in items)
+    return torch.from_numpy(np.frombuffer(raw, dtype=np.uint8).copy()).to(dev)
 
 
 class FusedTrainer:
     def __init__(self, model: HumanRF, lr: float = 1e-2, betas=(0.9, 0.99), eps: float = 1e-15, lr_decay: float = 0.5,
                  max_steps: int = 50001, bce_loss_weight: float = 1e-3, huber_delta: float = 0.01,
                  render_step_size: float = 4e-4, world_size: int = 1, process_group=None, prune: bool = True,
-                 seed: int = 123, overlap_allreduce: bool = True):
+                 seed: int = 123, reuse: str = "feat", exchange: str = "p2p", overlap_allreduce=None):
+        if reuse not in ("none", "feat", "feat+grid"):
+            raise ValueError("reuse must be 'none', 'feat' or 'feat+grid'")
+        if exchange not in ("p2p", "nccl"):
+            raise ValueError("exchange must be 'p2p' or 'nccl'")
         self.model, self.lr, self.betas, self.eps = model, lr, betas, eps
         self.lr_decay, self.max_steps = lr_decay, max_steps
         self.bce_w, self.delta, self.step_size = bce_loss_weight, huber_delta, render_step_size
-        self.world, self.pg, self.prune = world_size, process_group, prune
-        self.overlap_allreduce = overlap_allreduce
+        self.world, self.pg, self.prune, self.reuse = world_size, process_group, prune, reuse
+        self.exchange = exchange if world_size > 1 else "local"
+        self.rank = dist.get_rank(process_group) if world_size > 1 else 0
         self.params: List[torch.nn.Parameter] = model.hot_parameters()
         dev = self.params[0].device
-        m = model
-        S = m.num_segments
-        # Bucket layout, GRID-MAJOR: [grid 0 of every segment | grid 1 ... | grid 2 ... | grid 3 ... | vectors of every
-        # segment, MLPs, camera embeddings].  Region k is complete as soon as the scatter launch of grid k has run, so under
-        # data parallelism its all-reduce overlaps the scatter of grid k+1 (hot_parameters() itself is segment-major).
+        self.dev = dev
+        S = model.num_segments
+        # Bucket layout (grid-major: [grid 0 of every segment | grid 1 ... | grid 3 ... | vectors, MLPs, embeddings])
         self.slices, self.regions, self.adam_order = grid_major_bucket_layout([p.numel() for p in self.params], S)
         total = self.regions[-1][1]
-        self.grad = torch.zeros(total, dtype=torch.float32, device=dev)       # the all-reduce bucket
+        self._peer_ptrs: List[int] = []
+        lib = L.lib()
+        if self.exchange == "p2p":
+            self.grad = self._peer_buffer(total * 4).view(torch.float32)      # peers read it
+        else:
+            self.grad = torch.zeros(total, dtype=torch.float32, device=dev)   # the all-reduce bucket
         self.exp_avg = torch.zeros(total, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(total, dtype=torch.float32, device=dev)
         self.grad_views = [self.grad[a:b] for a, b in self.slices]
         self.t = 0                                  # optimiser steps taken (drives the learning-rate schedule)
-        self.steps = [0] * len(self.params)         # torch.optim.Adam's per-parameter state['step'] (bias corrections)
+        self.steps_dev = torch.zeros(len(self.params), dtype=torch.int32, device=dev)   # torch.optim.Adam's state['step']
+        self.active_dev = torch.ones(max(S, 1), dtype=torch.int32, device=dev)          # segment touched by this step
         self.gen = torch.Generator(device=dev).manual_seed(seed)
         self.nat = model.native()
+        if self.exchange == "p2p":
+            self._adopt_peer_shadows()
         sg = (L.SegmentGrads * S)()
         for s_ in range(S):
             for k in range(4):
                 sg[s_].grid[k] = self.grad_views[5 * s_ + k].data_ptr()
             sg[s_].vectors = self.grad_views[5 * s_ + 4].data_ptr()
-        self.sg_dev = torch.from_numpy(np.frombuffer(bytes(sg), dtype=np.uint8).copy()).to(dev)
+        self.sg_dev = _device_struct_array([sg], dev)
         i = 5 * S
         self.mlp_grad = self.grad[self.slices[i][0]:self.slices[i + 1][1]]   # sigma params then colour params, contiguous
         assert self.mlp_grad.numel() == model.mlp_grad_elems
         self.emb_grad = self.grad_views[i + 2] if model.camera_embedding_dim > 0 else None
+        dst, src = mlp_blob_permutation(model.camera_embedding_dim)
+        perm = np.zeros(model.mlp_grad_elems, np.int32)
+        perm[src] = dst
+        self.blob_perm = torch.from_numpy(perm).to(dev)
+        self._build_descriptors()
         self.last = {}
         self.profile = False
+        self.keep_grad = False       # tests: leave the step's gradient in self.grad (cleared before the next backward instead)
+        if self.world > 1:
+            self._bar = torch.zeros(1 + S, dtype=torch.float32, device=dev)
+
+    # ---------------------------------------------------------------------------------------------- set-up
+    def _peer_buffer(self, nbytes: int) -> torch.Tensor:
+        p = C.c_void_p()
+        L.check(L.lib().hrf_peer_alloc(int(nbytes), C.byref(p)))
+        self._peer_ptrs.append(p.value)
+        return torch.as_tensor(_RawCuda(p.value, int(nbytes)), device=self.dev)
+
+    def _exchange_handles(self, local: torch.Tensor) -> List[int]:
+        """Every rank's device address of the same buffer (CUDA IPC; own entry = local pointer)."""
+        lib = L.lib()
+        h = (C.c_ubyte * 64)()
+        L.check(lib.hrf_peer_export(local.data_ptr(), h))
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(h), group=self.pg)
+        out = []
+        for r, hb in enumerate(handles):
+            if r == self.rank:
+                out.append(local.data_ptr())
+            else:
+                p = C.c_void_p()
+                L.check(lib.hrf_peer_open((C.c_ubyte * 64).from_buffer_copy(hb), C.byref(p)))
+                out.append(p.value)
+        return out
+
+    def _adopt_peer_shadows(self) -> None:
+        """Move the bf16 shadow tables into ONE peer-visible buffer (the owners of the slices write into it remotely)."""
+        m, nat = self.model, self.nat
+        sizes = [g.numel() for fg in m.feature_grids for g in fg.grids()]
+        self.shadow_offsets = np.concatenate(([0], np.cumsum(sizes))).astype(np.int64)
+        self.shadow_flat = self._peer_buffer(int(self.shadow_offsets[-1]) * 2).view(torch.bfloat16)
+        views, j = [], 0
+        for s_, fg in enumerate(m.feature_grids):
+            row = []
+            for k in range(4):
+                v = self.shadow_flat[int(self.shadow_offsets[j]):int(self.shadow_offsets[j + 1])]
+                v.copy_(nat.shadows[s_][k])
+                row.append(v)
+                j += 1
+            views.append(row)
+        nat.adopt_shadows(views)
+        self.peer_grad = self._exchange_handles(self.grad)
+        self.peer_shadow = self._exchange_handles(self.shadow_flat)
+
+    def _build_descriptors(self) -> None:
+        m, nat, S = self.model, self.nat, self.model.num_segments
+        blob_ptr = nat.blob.data_ptr()
+        n_sig = MLP_SIGMA_PARAMS
+        p2p = self.exchange == "p2p"
+        items, first = [], 0
+        for i in self.adam_order:
+            p = self.params[i]
+            a, b = self.slices[i]
+            is_grid = i < 5 * S and i % 5 < 4
+            seg_flag = self.active_dev[i // 5:].data_ptr() if (i < 5 * S and S > 1) else None
+            step_ptr = self.steps_dev[i:].data_ptr()
+            shadow, perm = None, None
+            if is_grid:
+                shadow = nat.shadows[i // 5][i % 5].data_ptr()
+            elif i == 5 * S:
+                shadow, perm = blob_ptr, self.blob_perm.data_ptr()
+            elif i == 5 * S + 1:
+                shadow, perm = blob_ptr, self.blob_perm[n_sig:].data_ptr()
+            if p2p:
+                t = L.DpTensor()
+                t.param, t.exp_avg, t.exp_avg_sq = p.data_ptr(), self.exp_avg[a:b].data_ptr(), self.exp_avg_sq[a:b].data_ptr()
+                t.grad_offset, t.n = a, b - a
+                t.blob_perm, t.active, t.step = perm, seg_flag, step_ptr
+                if is_grid:
+                    j = 4 * (i // 5) + i % 5
+                    t.sharded, t.shadow_offset, t.local_shadow_bf16 = 1, int(self.shadow_offsets[j]), None
+                    t.shard_begin, t.shard_end = shard_bounds(b - a, self.rank, self.world, L.ADAM_BLOCK_ELEMS)
+                else:
+                    t.sharded, t.shadow_offset, t.local_shadow_bf16 = 0, -1, shadow
+                    t.shard_begin, t.shard_end = 0, b - a
+                t.first_block = first
+                first += (t.shard_end - t.shard_begin + L.ADAM_BLOCK_ELEMS - 1) // L.ADAM_BLOCK_ELEMS
+            else:
+                t = L.AdamTensor()
+                t.param, t.exp_avg, t.exp_avg_sq = p.data_ptr(), self.exp_avg[a:b].data_ptr(), self.exp_avg_sq[a:b].data_ptr()
+                t.grad, t.shadow_bf16, t.blob_perm = self.grad[a:b].data_ptr(), shadow, perm
+                t.active, t.step, t.n, t.first_block = seg_flag, step_ptr, b - a, first
+                first += (b - a + L.ADAM_BLOCK_ELEMS - 1) // L.ADAM_BLOCK_ELEMS
+            items.append(t)
+        self.adam_desc = _device_struct_array(items, self.dev)
+        self.adam_blocks = int(first)
+        if p2p:
+            self.peers = L.DpPeers()
+            for r in range(self.world):
+                self.peers.grad[r], self.peers.shadow[r] = self.peer_grad[r], self.peer_shadow[r]
+            self.peers.world, self.peers.rank = self.world, self.rank
+
+    @property
+    def steps(self) -> List[int]:
+        """torch.optim.Adam's per-parameter state['step'], in hot_parameters() order (reads the device counters)."""
+        return [int(x) for x in self.steps_dev.cpu().tolist()]
+
+    def gather_master_parameters(self) -> None:
+        """exchange="p2p" shards the fp32 masters of the hash tables over the ranks: bring every rank's copy of every
+        table up to date (before state_dict() / the autograd route).  Collective."""
+        if self.exchange != "p2p":
+            return
+        S = self.model.num_segments
+        with torch.no_grad():
+            for i in range(5 * S):
+                if i % 5 == 4:
+                    continue
+                flat = self.params[i].view(-1)
+                for r in range(self.world):
+                    a, b = shard_bounds(flat.numel(), r, self.world, L.ADAM_BLOCK_ELEMS)
+                    if b > a:
+                        dist.broadcast(flat[a:b], src=dist.get_global_rank(self.pg, r) if self.pg is not None else r, group=self.pg)
 
     # ----------------------------------------------------------------------------------------------
     def current_lr(self) -> float:
@@ -76,8 +231,9 @@ class FusedTrainer:
 
     def step(self, o, d, frames, t, ri, rgba, num_rays: int, kernel_event=None, return_loss: bool = False,
              background: Optional[torch.Tensor] = None, cameras: Optional[torch.Tensor] = None, bwd_events=None):
-        """One optimisation step on a ray batch given in InputBatch layout (device tensors).
-        Returns the number of kernels launched, or the loss value when return_loss."""
+        """One optimisation step on a ray batch given in InputBatch layout (device tensors).  Nothing in here reads
+        the device back: the step is enqueued and the call returns.  Returns the number of kernels launched, or the
+        loss value when return_loss (that one read is the caller's choice)."""
         lib, nat, dev = L.lib(), self.model.native(), t.device
         launches = 0
         marks = [] if self.profile else None
@@ -91,144 +247,135 @@ class FusedTrainer:
         mark("start")
         step = self.step_size
         t = t.reshape(-1)
-        # Segments this batch touches (humanrf.py:162-179): the reference gives the others no gradient, so Adam leaves
-        # their parameters, moments and step counters alone.  Decided on the device; read back with the prune counter.
         S = self.model.num_segments
-        used = None
+        cams = cameras if self.model.camera_embedding_dim > 0 else None
+        # Segments this batch touches (humanrf.py:162-179): the reference gives the others no gradient, so Adam leaves
+        # their parameters, moments and step counters alone.  Decided AND consumed on the device.
         if S > 1:
-            used = active_segments(self.model.frame_numbers_to_segment_numbers, frames, S).to(torch.int64)
-            if self.world > 1:                       # a segment is active if any rank's batch touches it
-                dist.all_reduce(used, op=dist.ReduceOp.MAX, group=self.pg)
-        active = None
+            used = active_segments(self.model.frame_numbers_to_segment_numbers, frames, S)
+            if self.world == 1:
+                self.active_dev.copy_(used)
+            launches += 8
+        loss_scale = None
+        if self.world > 1:                              # this rank's share of the union batch (humanrf_b200/parallel.py)
+            loss_scale = union_batch_loss_scale(num_rays, dev, self.pg).reshape(1).float().contiguous()
+            launches += 2
+        src = feat_src = None
+        n_cap = t.shape[0]
+        count = None
         # ---- prune_samples (volume_rendering.py:42-84): jitter, density-only pass, visibility compaction
         if self.prune:
             t = t + torch.rand(t.shape, device=dev, generator=self.gen) * step
-            n0 = t.shape[0]
             off0 = ray_offsets(ri, num_rays)
-            sigma0 = nat.density_early_stop(nat.samples_rays(o, d, frames, t, ri), off0, num_rays, step)
-            keep = torch.empty(n0, dtype=torch.uint8, device=dev)
+            s0 = nat.samples_rays(o, d, frames, t, ri)
+            if self.reuse == "none":
+                sigma0 = nat.density_early_stop(s0, off0, num_rays, step)
+            else:
+                sigma0, feat_src = nat.density_early_stop(s0, off0, num_rays, step, save=self.reuse)
+            keep = torch.empty(n_cap, dtype=torch.uint8, device=dev)
             kept_off = torch.empty(num_rays + 1, dtype=torch.int32, device=dev)
-            t2 = torch.empty(n0, dtype=torch.float32, device=dev)
-            ri2 = torch.empty(n0, dtype=torch.int64, device=dev)
-            counter = torch.zeros(1, dtype=torch.int64, device=dev)
+            t2 = torch.empty(n_cap, dtype=torch.float32, device=dev)
+            ri2 = torch.empty(n_cap, dtype=torch.int64, device=dev)
+            src = torch.empty(n_cap, dtype=torch.int32, device=dev) if feat_src is not None else None
+            count = torch.zeros(1, dtype=torch.int64, device=dev)
             L.check(lib.hrf_prune(sigma0.data_ptr(), t.data_ptr(), ri.data_ptr(), off0.data_ptr(), num_rays, step, 1e-4,
-                                  1e-4, keep.data_ptr(), kept_off.data_ptr(), t2.data_ptr(), ri2.data_ptr(),
-                                  counter.data_ptr(), L.stream()))
-            mark("prune_enqueued")
-            if used is None:
-                kept = int(counter.item())
-            else:                                    # one read for both
-                host = torch.cat((counter, used)).cpu().tolist()
-                kept, active = int(host[0]), [bool(x) for x in host[1:]]
-            t, ri = t2[:kept], ri2[:kept]
+                                  1e-4, keep.data_ptr(), kept_off.data_ptr(), t2.data_ptr(), ri2.data_ptr(), L.ptr(src),
+                                  count.data_ptr(), L.stream()))
+            t, ri, off = t2, ri2, kept_off                  # hrf_prune's scan IS the ray-offset table of the survivors
             launches += 9
-            mark("prune_synced")
-            off = kept_off                                   # hrf_prune's scan IS the ray-offset table of the survivors
-        if used is not None and active is None:
-            active = [bool(x) for x in used.cpu().tolist()]
-        n = t.shape[0]
-        # ---- forward: fused field + compositing
-        samples = nat.samples_rays(o, d, frames, t, ri, cameras if self.model.camera_embedding_dim > 0 else None)
-        sigma, _, rgb, feat = nat.forward(samples, 1, want_geo=False, want_feat=True)
+            mark("prune")
+        else:
+            off = ray_offsets(ri, num_rays)
+            launches += 1
+        # ---- forward: fused field + compositing (survivor count read from the device by the kernels)
+        samples = nat.samples_rays(o, d, frames, t, ri, cams, count_dev=count)
+        if feat_src is not None:
+            sigma, rgb = nat.forward_from_features(samples, feat_src, src)
+            feat, egrid, egrid_stride = feat_src, (feat_src.data_ptr() + 64 * n_cap if self.reuse == "feat+grid" else None), n_cap
+        else:
+            sigma, _, rgb, feat = nat.forward(samples, 1, want_geo=False, want_feat=True)
+            egrid, egrid_stride = feat.data_ptr() + 64 * n_cap, n_cap
         if kernel_event is not None:
             kernel_event.record()
         mark("forward")
-        if not self.prune:
-            off = ray_offsets(ri, num_rays)
         bg = background if background is not None else torch.rand((num_rays, 3), device=dev, generator=self.gen)  # trainer.py:237
         color = torch.empty((num_rays, 3), dtype=torch.float32, device=dev)
         wsum = torch.empty((num_rays, 1), dtype=torch.float32, device=dev)
         L.check(lib.hrf_composite_forward(sigma.data_ptr(), rgb.data_ptr(), t.data_ptr(), off.data_ptr(), num_rays, step,
                                           bg.data_ptr(), color.data_ptr(), wsum.data_ptr(), None, L.stream()))
-        # ---- loss on the [R,3] outputs (tiny): Huber + BCE, gradients by autograd on the leaf outputs
-        color.requires_grad_(True)
-        wsum.requires_grad_(True)
-        mask = rgba[:, 3:4]
-        gt = rgba[:, :3] * mask + bg * (1 - mask)
-        photo = torch.nn.functional.huber_loss(color, gt, delta=self.delta, reduction="mean")
-        pc = torch.clamp(wsum, min=0, max=1)
-        bce = -(mask * torch.log(pc + 1e-10) + (1 - mask) * torch.log(1 - pc + 1e-10))
-        loss = photo + bce.mean() * self.bce_w
-        # data parallel: weight by this rank's share of the union batch (humanrf_b200/parallel.py)
-        (loss * union_batch_loss_scale(num_rays, dev, self.pg) if self.world > 1 else loss).backward()
-        mark("composite+loss")
-        # ---- backward: compositing, then the fused field backward into the flat bucket
-        d_sigma = torch.empty(n, dtype=torch.float32, device=dev)
-        d_rgb = torch.empty((n, 3), dtype=torch.float32, device=dev)
+        # ---- loss (Huber + BCE) and its gradient w.r.t. the [R,3] / [R] outputs in one launch
+        d_color = torch.empty((num_rays, 3), dtype=torch.float32, device=dev)
+        d_wsum = torch.empty(num_rays, dtype=torch.float32, device=dev)
+        loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        rgba = rgba if (rgba.dtype == torch.float32 and rgba.is_contiguous()) else rgba.float().contiguous()
+        L.check(lib.hrf_train_loss(color.data_ptr(), wsum.data_ptr(), rgba.data_ptr(), bg.data_ptr(), num_rays, self.delta,
+                                   self.bce_w, L.ptr(loss_scale), d_color.data_ptr(), d_wsum.data_ptr(), loss.data_ptr(),
+                                   L.stream()))
+        # ---- backward: compositing, then the fused field backward into the flat bucket (clean: Adam re-zeroes it)
+        d_sigma = torch.empty(n_cap, dtype=torch.float32, device=dev)
+        d_rgb = torch.empty((n_cap, 3), dtype=torch.float32, device=dev)
         L.check(lib.hrf_composite_backward(sigma.data_ptr(), rgb.data_ptr(), t.data_ptr(), off.data_ptr(), num_rays, step,
-                                           bg.data_ptr(), color.grad.data_ptr(), wsum.grad.reshape(-1).data_ptr(),
-                                           d_sigma.data_ptr(), d_rgb.data_ptr(), L.stream()))
-        self.grad.zero_()
+                                           bg.data_ptr(), d_color.data_ptr(), d_wsum.data_ptr(), d_sigma.data_ptr(),
+                                           d_rgb.data_ptr(), L.stream()))
+        mark("composite+loss")
         if bwd_events is not None:
             bwd_events[0].record()
-        ws = torch.empty(n * 40, dtype=torch.float32, device=dev)   # 160 B / sample
-        L.check(lib.hrf_field_backward_mlp(C.byref(nat.field), C.byref(samples), d_sigma.data_ptr(), d_rgb.data_ptr(),
-                                           feat.data_ptr(), self.mlp_grad.data_ptr(), L.ptr(self.emb_grad), ws.data_ptr(),
-                                           L.stream()))
-        egrid = feat.data_ptr() + 64 * n
-        works = None
-        # data parallel: only the gradients of the segments this step touched (on any rank) are reduced
-        spans = allreduce_spans(self.slices, self.regions, S, active) if self.world > 1 else None
-        if self.world == 1 or not self.overlap_allreduce:
-            L.check(lib.hrf_field_backward_tables(C.byref(nat.field), C.byref(samples), self.sg_dev.data_ptr(), egrid,
-                                                  ws.data_ptr(), 0, 4, L.stream()))
-            if self.world > 1 and active is None:
-                allreduce_bucket_(self.grad, self.pg)                       # everything is active: one message
-            elif self.world > 1:
-                for region in spans:
-                    for a, b in region:
-                        allreduce_bucket_(self.grad[a:b], self.pg)
-            launches += 8 + 12 + ((1 if active is None else sum(len(r) for r in spans)) if self.world > 1 else 0)
-        else:
-            # table k's gradient region is reduced (NCCL, its own stream) while table k+1 is still being scattered; the
-            # sum's mean over ranks is folded into Adam's grad_scale
-            works = []
-            for k in range(4):
-                L.check(lib.hrf_field_backward_tables(C.byref(nat.field), C.byref(samples), self.sg_dev.data_ptr(), egrid,
-                                                      ws.data_ptr(), k, 1, L.stream()))
-                works.append([allreduce_bucket_(self.grad[a:b], self.pg, async_op=True) for a, b in spans[k]])
-            works.append([allreduce_bucket_(self.grad[a:b], self.pg, async_op=True) for a, b in spans[4]])
-            launches += 8 + 15 + sum(len(r) for r in spans)
+        if self.keep_grad:
+            self.grad.zero_()
+        ws = torch.empty(n_cap * 40, dtype=torch.float32, device=dev)   # 160 B / sample
+        L.check(lib.hrf_field_backward_mlp(C.byref(nat.field), C.byref(samples), d_sigma.data_ptr(), d_rgb.data_ptr(), None,
+                                           feat.data_ptr(), L.ptr(src), self.mlp_grad.data_ptr(), L.ptr(self.emb_grad),
+                                           ws.data_ptr(), L.stream()))
+        mark("backward_mlp")
+        L.check(lib.hrf_field_backward_tables(C.byref(nat.field), C.byref(samples), self.sg_dev.data_ptr(), egrid, L.ptr(src),
+                                              egrid_stride, ws.data_ptr(), 0, 4, L.stream()))
+        launches += 8
         if bwd_events is not None:
             bwd_events[1].record()
-        mark("backward")
-        self.apply_adam(1.0 / self.world, works, active)
-        launches += len(self.params) + 3
-        mark("allreduce+adam")
-        self.last = {"samples": n, "loss": loss.detach()}
-        if marks is not None:
-            torch.cuda.synchronize()
-            self.last["phases_ms"] = {b[0]: a[1].elapsed_time(b[1]) for a, b in zip(marks[:-1], marks[1:])}
+        mark("scatter")
+        launches += self._exchange_and_adam(used if S > 1 else None)
+        mark("exchange+adam")
+        self.last = {"samples": count[0] if count is not None else n_cap, "loss": loss[0], "marks": marks}
         if return_loss:
             return float(loss.item())
         return launches
 
-    def apply_adam(self, grad_scale: float, works=None, active=None) -> None:
-        """Adam over the bucket in region order; `works` = the pending all-reduces of each of the 5 regions (a list per
-        region), waited for just before the first parameter of that region.  `active` (bool per segment, None = all) selects the segments
-        that took part in this step: the others are skipped entirely and keep their own step counters, exactly what
-        torch.optim.Adam does with parameters whose .grad is None (the reference's trainer.py:174,251)."""
-        nat = self.nat
+    def _exchange_and_adam(self, used) -> int:
+        lib = L.lib()
         lr = self.current_lr()
         self.t += 1
+        b1, b2 = self.betas
+        if self.world == 1:
+            L.check(lib.hrf_adam_multi(self.adam_desc.data_ptr(), len(self.params), self.adam_blocks, lr, b1, b2, self.eps, 1.0,
+                                       0 if self.keep_grad else 1, L.stream()))
+            return 2
         S = self.model.num_segments
-        with torch.no_grad():
-            for j, i in enumerate(self.adam_order):
-                region = min(j // S, 4)
-                if works is not None and works[region]:
-                    for w in works[region]:
-                        w.wait()
-                    works[region] = []
-                if active is not None and i < 5 * S and not active[i // 5]:
-                    continue
-                self.steps[i] += 1
-                shadow = nat.shadows[i // 5][i % 5] if (i < 5 * S and i % 5 < 4) else None
-                self._adam(i, shadow, lr, grad_scale)
-            nat.repack_mlp()
+        # barrier A (all ranks' gradients are complete) carrying the union of the active-segment flags
+        self._bar.zero_()
+        if used is not None:
+            self._bar[1:] = used.float()
+        dist.all_reduce(self._bar, group=self.pg)
+        if used is not None:
+            self.active_dev.copy_(self._bar[1:] > 0)
+        if self.exchange == "nccl":
+            dist.all_reduce(self.grad, group=self.pg)
+            L.check(lib.hrf_adam_multi(self.adam_desc.data_ptr(), len(self.params), self.adam_blocks, lr, b1, b2, self.eps,
+                                       1.0 / self.world, 1, L.stream()))
+            return 6
+        L.check(lib.hrf_dp_reduce_adam(C.byref(self.peers), self.adam_desc.data_ptr(), len(self.params), self.adam_blocks, lr, b1,
+                                       b2, self.eps, 1.0 / self.world, L.stream()))
+        # barrier B: every peer has read this rank's bucket and written this rank's shadow slices
+        dist.all_reduce(self._bar[:1], group=self.pg)
+        self.grad.zero_()
+        return 7
 
-    def _adam(self, i: int, shadow: Optional[torch.Tensor], lr: float, grad_scale: float) -> None:
-        p = self.params[i]
-        a, b = self.slices[i]
-        L.check(L.lib().hrf_adam_step(p.data_ptr(), self.exp_avg[a:b].data_ptr(), self.exp_avg_sq[a:b].data_ptr(),
-                                      self.grad[a:b].data_ptr(), L.ptr(shadow), b - a, lr, self.betas[0], self.betas[1],
-                                      self.eps, self.steps[i], grad_scale, L.stream()))
+    def close(self) -> None:
+        """Releases the peer-visible buffers (exchange="p2p").  Collective-free; call after the last step."""
+        if self.exchange == "p2p" and self._peer_ptrs:
+            torch.cuda.synchronize()
+            lib = L.lib()
+            for r in range(self.world):
+                if r != self.rank:
+                    lib.hrf_peer_close(self.peer_grad[r])
+                    lib.hrf_peer_close(self.peer_shadow[r])
+            self._peer_ptrs = []      # the buffers themselves stay alive as long as tensors view them (process lifetime)

@@ -77,7 +77,7 @@ def prune_samples(input_batch: InputBatch, scene_representation: HumanRF, is_tra
     counter = torch.zeros(1, dtype=torch.int64, device=dev)
     L.check(L.lib().hrf_prune(sigma.data_ptr(), t.data_ptr(), ri.data_ptr(), off.data_ptr(), num_rays,
                               float(render_step_size), 1e-4, 1e-4, keep.data_ptr(), kept_off.data_ptr(),
-                              out_t.data_ptr(), out_ri.data_ptr(), counter.data_ptr(), L.stream()))
+                              out_t.data_ptr(), out_ri.data_ptr(), None, counter.data_ptr(), L.stream()))
     kept = int(counter.item())
     ib.sample_distances = out_t[:kept].view(-1, 1)
     ib.ray_indices = out_ri[:kept]

@@ -142,6 +142,11 @@ typedef struct {
   const int32_t* camera_numbers;     /* query form: [N] */
   const int32_t* ray_camera_numbers; /* ray-batch form: [R] */
   int32_t use_camera_embeddings;
+  /* Sync-free pipelines: when non-NULL the kernels read the LIVE number of samples from this device scalar and
+   * num_samples is the capacity of the per-sample arrays (grid sizing, strides of the [..][N] buffers).  This is what
+   * lets a training step prune on the device and keep going without reading the survivor count back
+   * (the reference reads it implicitly through boolean-mask indexing, volume_rendering.py:83-84). */
+  const int64_t* num_samples_dev;
 } hrf_samples;
 
 /* mode: 0 = density only (sigma, geo), 1 = density + radiance.  Any output may be NULL.
@@ -153,6 +158,14 @@ int hrf_field_forward(const hrf_field* f, const hrf_samples* s, int mode, int ml
                       void* grid_feat_bf16 /* [64,N] bf16x2 per-(level,grid) interpolated features for backward, or NULL */,
                       void* stream);
 
+/* The MLP half of hrf_field_forward for samples whose composed features already exist (the density-only pass of
+ * prune_samples encodes every candidate; the render pass of the survivors does not have to encode them again):
+ * feat_in_bf16 [M,32] as written by a previous pass, feat_index[i] = its row for sample i (NULL = identity).
+ * `s` must be in ray-batch form (view directions / camera numbers are read through ray_indices). */
+int hrf_field_forward_from_features(const hrf_field* f, const hrf_samples* s, const void* feat_in_bf16,
+                                    const int32_t* feat_index, float* sigma /* [N] */, float* rgb /* [N,3] */,
+                                    void* stream);
+
 /* Density-only pass of prune_samples (volume_rendering.py:66-84) with an exact early stop: ray chunks are
  * evaluated front to back; once a ray's accumulated optical depth makes every later sample fail nerfacc's
  * transmittance test (T < 1e-4) those samples are reported with sigma = 0 without being evaluated.  The kept
@@ -162,6 +175,8 @@ int64_t hrf_density_early_stop_workspace_bytes(int64_t num_rays);
 int hrf_field_density_early_stop(const hrf_field* f, const hrf_samples* s /* ray-batch form */,
                                  const int32_t* ray_offsets /* [R+1] */, int64_t num_rays, float step,
                                  float stop_depth /* > -ln(1e-4); 9.4 recommended */, float* sigma /* [N] */,
+                                 void* feat_bf16 /* [N,32] composed features of every evaluated sample, or NULL */,
+                                 void* grid_feat_bf16 /* [64,N] per-(level,grid) features, or NULL */,
                                  void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -176,7 +191,8 @@ int hrf_ray_offsets(const int64_t* ray_indices, int64_t num_samples, int64_t num
 int hrf_prune(const float* sigma, const float* sample_distances, const int64_t* ray_indices,
               const int32_t* ray_offsets, int64_t num_rays, float step, float early_stop_eps, float alpha_thre,
               uint8_t* keep_mask /* [N] or NULL */, int32_t* kept_offsets /* [R+1] */,
-              float* out_distances, int64_t* out_ray_indices, int64_t* counters, void* stream);
+              float* out_distances, int64_t* out_ray_indices, int32_t* out_source_index /* [N] index of each kept sample
+              in the input arrays, or NULL */, int64_t* counters, void* stream);
 /* render: w_i = exp(-sum_{j<i} sigma_j*dt_j) * (1-exp(-sigma_i*dt_i)), dt=(t+step)-t;
  * color = sum w*rgb (+ background*(1-sum w)), weights_sum = sum w. background: [R,3] or NULL. */
 int hrf_composite_forward(const float* sigma, const float* rgb, const float* sample_distances,
@@ -201,8 +217,11 @@ typedef struct {
 
 int hrf_field_backward(const hrf_field* f, const hrf_samples* s, const hrf_segment_grads* seg_grads /* device array */,
                        const float* d_sigma /* [N] */, const float* d_rgb /* [N,3] or NULL */,
-                       const void* feat_bf16 /* [N,32] from hrf_field_forward, or NULL to re-encode */,
-                       const void* grid_feat_bf16 /* [64,N] from hrf_field_forward, or NULL to re-gather the tables */,
+                       const float* d_geo /* [N,15] gradient of the geometry features, or NULL */,
+                       const void* feat_bf16 /* composed features from a forward pass, or NULL to re-encode */,
+                       const void* grid_feat_bf16 /* [64,stride] from a forward pass, or NULL to re-gather the tables */,
+                       const int32_t* feat_index /* row of sample i in feat / grid_feat (NULL = identity) */,
+                       int64_t grid_feat_stride /* row length of grid_feat (0 = num_samples) */,
                        float* d_mlp /* fp32 [3072 + 64*color_in_width + 5120]: sigma W1,W2, colour W1,W2,W3 row-major [out,in] */,
                        float* d_camera_embeddings /* fp32 [num_cameras, dim] accumulated into, or NULL */,
                        void* workspace /* 160 bytes per sample (16-byte aligned): d(features) level-major, positions, segment ids */, void* stream);
@@ -210,9 +229,23 @@ int hrf_field_backward(const hrf_field* f, const hrf_samples* s, const hrf_segme
  * next table's scatter still runs: hrf_field_backward == hrf_field_backward_mlp + hrf_field_backward_tables(0, 4).
  * Table k's gradient is complete after the launch covering grid k; the vector gradients after the last launch. */
 int hrf_field_backward_mlp(const hrf_field* f, const hrf_samples* s, const float* d_sigma, const float* d_rgb,
-                           const void* feat_bf16, float* d_mlp, float* d_camera_embeddings, void* workspace, void* stream);
+                           const float* d_geo, const void* feat_bf16, const int32_t* feat_index, float* d_mlp,
+                           float* d_camera_embeddings, void* workspace, void* stream);
 int hrf_field_backward_tables(const hrf_field* f, const hrf_samples* s, const hrf_segment_grads* seg_grads,
-                              const void* grid_feat_bf16, const void* workspace, int grid_first, int grid_count, void* stream);
+                              const void* grid_feat_bf16, const int32_t* feat_index, int64_t grid_feat_stride,
+                              const void* workspace, int grid_first, int grid_count, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Training loss on the per-ray outputs, forward and backward in one launch (trainer.py:205-215,229-238,
+ * utils/loss.py:4-10): gt = rgb*mask + background*(1-mask); HuberLoss(delta, mean) over [R,3] +
+ * bce_weight * mean(BCE(clamp(weights_sum,0,1), mask)) with eps 1e-10.  loss_out[0] += loss (caller zeroes);
+ * d_color / d_weights_sum are d(loss * *loss_scale_dev) (loss_scale_dev NULL = 1: data-parallel ranks weight their
+ * share of the union batch with it).
+ * ---------------------------------------------------------------------------------------- */
+int hrf_train_loss(const float* color /* [R,3] */, const float* weights_sum /* [R] */, const float* rgba /* [R,4] */,
+                   const float* background /* [R,3] */, int64_t num_rays, float huber_delta, float bce_weight,
+                   const float* loss_scale_dev, float* d_color /* [R,3] */, float* d_weights_sum /* [R] */,
+                   float* loss_out /* [1], accumulated */, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * tensor_composition_native parity (tensor_composition.cu:120-219): stand-alone fwd/bwd of
@@ -235,6 +268,64 @@ int hrf_adam_step(float* param, float* exp_avg, float* exp_avg_sq, const float* 
                   int64_t n, float lr, float beta1, float beta2, float eps, int step, float grad_scale,
                   void* stream);
 int hrf_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
+
+/* All parameter tensors of a model in ONE launch (the per-tensor entry point above costs one launch per tensor: 23
+ * for a single segment).  tensors: device array of descriptors; a tensor whose *active flag is 0 is skipped entirely
+ * -- parameters, moments AND its step counter -- which is what torch.optim.Adam does with a parameter whose .grad is
+ * None (the reference gives untouched temporal segments no gradient, humanrf.py:162-179, trainer.py:174).  Step
+ * counters live on the device (int32 per tensor, incremented here), so a step needs no host decision.  After reading
+ * a gradient element the kernel writes 0 back when zero_grad != 0 (the bucket is then clean for the next backward).
+ * blob_perm: for the MLP tensors, element i of the tensor is also written as bf16 to shadow[blob_perm[i]] (the packed
+ * tcgen05 weight blob) instead of shadow[i]. */
+typedef struct {
+  float* param; float* exp_avg; float* exp_avg_sq; float* grad;
+  void* shadow_bf16;                 /* or NULL */
+  const int32_t* blob_perm;          /* or NULL */
+  const int32_t* active;             /* device flag (segment used by this step) or NULL = always active */
+  int32_t* step;                     /* device step counter of this tensor */
+  int64_t n;
+  int64_t first_block;               /* exclusive prefix of ceil(n / HRF_ADAM_BLOCK_ELEMS) over the tensors */
+} hrf_adam_tensor;
+#define HRF_ADAM_BLOCK_ELEMS 4096
+int hrf_adam_multi(const hrf_adam_tensor* tensors /* device */, int num_tensors, int64_t total_blocks, float lr, float beta1,
+                   float beta2, float eps, float grad_scale, int zero_grad, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Data-parallel training (the reference is single-GPU, the step wrapped is trainer.py:250-253).
+ * One process per GPU.  Gradient buckets and bf16 shadow tables live in peer-visible device memory
+ * (hrf_peer_alloc + CUDA IPC handles exchanged by the host side); hrf_dp_reduce_adam is the whole exchange step in one
+ * kernel over NVLink peer memory: for this rank's 1/world slice of every sharded tensor it sums the gradient slices of
+ * all ranks (P2P loads, rank order), runs Adam on the local fp32 master / moments and stores the refreshed bf16 shadow
+ * entries into every rank's shadow buffer (P2P stores); replicated (small) tensors are reduced on every rank.  The
+ * caller brackets it with two cross-rank barriers (all gradients complete before; all shadows written / all buckets
+ * read after) and clears its own bucket afterwards.
+ * ---------------------------------------------------------------------------------------- */
+#define HRF_DP_MAX_WORLD 8
+int hrf_peer_alloc(int64_t bytes, void** ptr_out);        /* zero-filled, exportable (not from a pooled allocator) */
+int hrf_peer_free(void* ptr);
+int hrf_peer_export(void* ptr, void* handle_out64 /* 64 bytes, host */);
+int hrf_peer_open(const void* handle64, void** ptr_out);  /* a handle exported by ANOTHER process */
+int hrf_peer_close(void* ptr);
+typedef struct {
+  float* grad[HRF_DP_MAX_WORLD];     /* every rank's gradient bucket (own entry = local pointer) */
+  void*  shadow[HRF_DP_MAX_WORLD];   /* every rank's flat bf16 shadow buffer */
+  int32_t world, rank;
+} hrf_dp_peers;
+typedef struct {
+  float* param; float* exp_avg; float* exp_avg_sq;   /* local tensors, full size (a sharded tensor only touches its slice) */
+  int64_t grad_offset;               /* element offset of the tensor inside every gradient bucket */
+  int64_t shadow_offset;             /* element offset inside every shadow buffer (sharded tensors), or -1 */
+  void* local_shadow_bf16;           /* replicated tensors: local bf16 copy / packed MLP blob, or NULL */
+  const int32_t* blob_perm;          /* as hrf_adam_tensor */
+  const int32_t* active;
+  int32_t* step;
+  int64_t n;
+  int64_t shard_begin, shard_end;    /* this rank's element range; [0, n) for replicated tensors */
+  int64_t first_block;               /* exclusive prefix of ceil((shard_end - shard_begin) / HRF_ADAM_BLOCK_ELEMS) */
+  int32_t sharded;
+} hrf_dp_tensor;
+int hrf_dp_reduce_adam(const hrf_dp_peers* peers /* host */, const hrf_dp_tensor* tensors /* device */, int num_tensors,
+                       int64_t total_blocks, float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Pre-processing that feeds the hot path.

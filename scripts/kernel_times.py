@@ -62,7 +62,7 @@ def main():
 
     def prune():
         L.check(lib.hrf_prune(sigma0.data_ptr(), g["t"].data_ptr(), g["ri"].data_ptr(), off0.data_ptr(), R, 4e-4, 1e-4, 1e-4,
-                              keep.data_ptr(), kept_off.data_ptr(), t2.data_ptr(), ri2.data_ptr(), counter.data_ptr(), L.stream()))
+                              keep.data_ptr(), kept_off.data_ptr(), t2.data_ptr(), ri2.data_ptr(), None, counter.data_ptr(), L.stream()))
 
     timeit("hrf_prune (visibility + scan + compact)", prune)
     n = int(counter.item())
@@ -87,13 +87,13 @@ def main():
     egrid = feat.data_ptr() + 64 * n
 
     def bwd_mlp():
-        L.check(lib.hrf_field_backward_mlp(C.byref(nat.field), C.byref(s), d_sigma.data_ptr(), d_rgb.data_ptr(), feat.data_ptr(),
-                                           d_mlp.data_ptr(), None, ws.data_ptr(), L.stream()))
+        L.check(lib.hrf_field_backward_mlp(C.byref(nat.field), C.byref(s), d_sigma.data_ptr(), d_rgb.data_ptr(), None, feat.data_ptr(),
+                                           None, d_mlp.data_ptr(), None, ws.data_ptr(), L.stream()))
 
     timeit("backward MLP kernel (saved feat)", bwd_mlp)
 
     def scatter(eg):
-        L.check(lib.hrf_field_backward_tables(C.byref(nat.field), C.byref(s), sg_dev.data_ptr(), eg, ws.data_ptr(), 0, 4, L.stream()))
+        L.check(lib.hrf_field_backward_tables(C.byref(nat.field), C.byref(s), sg_dev.data_ptr(), eg, None, 0, ws.data_ptr(), 0, 4, L.stream()))
 
     timeit("table scatter, saved egrid", lambda: scatter(egrid))
     timeit("table scatter, re-gather tables", lambda: scatter(None))

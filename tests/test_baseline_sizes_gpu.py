@@ -201,7 +201,7 @@ def test_table_scatter_matches_float64_autograd(cuda, pair):
         sg[s].vectors = grads[5 * s + 4].data_ptr()
     sg_dev = torch.from_numpy(np.frombuffer(bytes(sg), dtype=np.uint8).copy()).to(cuda)
     samples = nat.samples_query(pos.to(cuda), None, fr.to(cuda).to(torch.int32))
-    L.check(L.lib().hrf_field_backward_tables(C.byref(nat.field), C.byref(samples), sg_dev.data_ptr(), None, ws.data_ptr(),
+    L.check(L.lib().hrf_field_backward_tables(C.byref(nat.field), C.byref(samples), sg_dev.data_ptr(), None, None, 0, ws.data_ptr(),
                                               0, 4, L.stream()))
     torch.cuda.synchronize()
     for s in range(m.num_segments):

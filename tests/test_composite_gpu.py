@@ -37,9 +37,10 @@ def test_ray_offsets_and_prune(cuda):
         out_t = torch.empty(n, device=cuda)
         out_ri = torch.empty(n, dtype=torch.int64, device=cuda)
         counter = torch.zeros(1, dtype=torch.int64, device=cuda)
+        src = torch.empty(n, dtype=torch.int32, device=cuda)
         L.check(L.lib().hrf_prune(sigma.to(cuda).data_ptr(), t.data_ptr(), ri.data_ptr(), off.data_ptr(), nr, 4e-4, 1e-4,
                                   1e-4, keep.data_ptr(), kept_off.data_ptr(), out_t.data_ptr(), out_ri.data_ptr(),
-                                  counter.data_ptr(), L.stream()))
+                                  src.data_ptr(), counter.data_ptr(), L.stream()))
         exp = R.prune_mask(sigma, b["ri"]).numpy()
         got = keep.bool().cpu().numpy()
         # identical except where T or alpha sits within float rounding of the 1e-4 thresholds
@@ -51,6 +52,7 @@ def test_ray_offsets_and_prune(cuda):
         assert k == got.sum()
         np.testing.assert_array_equal(out_t[:k].cpu().numpy(), b["t"].numpy()[got])
         np.testing.assert_array_equal(out_ri[:k].cpu().numpy(), b["ri"].numpy()[got])
+        np.testing.assert_array_equal(src[:k].cpu().numpy(), np.nonzero(got)[0])          # where each survivor came from
         np.testing.assert_array_equal(kept_off.cpu().numpy(), np.concatenate(([0], np.cumsum(np.bincount(b["ri"].numpy()[got], minlength=nr)))))
 
 
@@ -132,7 +134,7 @@ def test_early_stop_density_pass_gives_the_same_kept_set(cuda):
             cnt = torch.zeros(1, dtype=torch.int64, device=cuda)
             L.check(L.lib().hrf_prune(sig.data_ptr(), g["t"].data_ptr(), g["ri"].data_ptr(), off.data_ptr(), 300, 4e-4, 1e-4,
                                       1e-4, keep.data_ptr(), kept_off.data_ptr(), ot.data_ptr(), ori.data_ptr(),
-                                      cnt.data_ptr(), L.stream()))
+                                      None, cnt.data_ptr(), L.stream()))
             masks.append(keep.clone())
         assert torch.equal(masks[0], masks[1])
         print(f"ragged={ragged}: {int(skipped.sum())} of {full.numel()} densities skipped, kept {int(masks[0].sum())}")

@@ -36,67 +36,98 @@ def _collect(q, procs, count, timeout=240):
     return out
 
 
-def _train(rank, world, port, spans, q, overlap=True):
+def _train(rank, world, port, spans, q, exchange="p2p", segs=(6,), frame_plan=None):
+    """frame_plan: per step, the frames the batch's rays are re-drawn from (multi-segment case: steps that touch only
+    some segments, and different segments on different ranks)."""
     import torch.distributed as dist
 
     from humanrf_b200.training import FusedTrainer
 
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
-    pg = None
     if world > 1:
         os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
-    model, frames = make_model((6,), table_std=0.5, device=dev)
+    model, frames = make_model(segs, table_std=0.5, device=dev)
     b = synthetic_rays(512, 48, frames, seed=4, ragged=True)
     bg_all = torch.rand(512, 3, generator=torch.Generator().manual_seed(9))
     lo, hi = spans[rank]
-    sb = {k: v.to(dev).contiguous() for k, v in _subset(b, lo, hi).items()}
-    tr = FusedTrainer(model, lr=1e-2, prune=False, world_size=world, overlap_allreduce=overlap)
-    for _ in range(STEPS):
+    tr = FusedTrainer(model, lr=1e-2, prune=False, world_size=world, exchange=exchange)
+    for step in range(STEPS):
+        if frame_plan is not None:
+            pool = torch.tensor(frame_plan[step], dtype=torch.int32)
+            h = pool.numel() // 2                                        # rays < 200 (rank 0's share) draw from the first half of
+            r_ = torch.arange(512)                                       # the pool, the others from the second: the two ranks
+            b["frames"] = torch.where(r_ < 200, pool[r_ % h], pool[h + r_ % (pool.numel() - h)])   # may touch DIFFERENT segments
+        sb = {k: v.to(dev).contiguous() for k, v in _subset(b, lo, hi).items()}
         tr.step(sb["o"], sb["d"], sb["frames"], sb["t"], sb["ri"], sb["rgba"], hi - lo, background=bg_all[lo:hi].to(dev))
+    tr.gather_master_parameters()      # exchange="p2p" shards the fp32 masters of the tables over the ranks
     torch.cuda.synchronize()
-    q.put((rank, [p.detach().cpu().numpy() for p in model.hot_parameters()]))
+    shadows = [s.float().cpu().numpy() for row in model.native().shadows for s in row]
+    q.put((rank, [p.detach().cpu().numpy() for p in model.hot_parameters()], shadows, tr.steps))
     if world > 1:
         dist.barrier()
+        tr.close()
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("overlap", [False, True])
-def test_two_rank_dp_equals_single_process(cuda, overlap):
-    """overlap=False: one all-reduce of the whole bucket after the backward; overlap=True: per-table all-reduces that
-    run beside the next table's scatter (FusedTrainer's default)."""
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    init = [p.detach().cpu().numpy() for p in make_model((6,), table_std=0.5, device=cuda)[0].hot_parameters()]
-    p = ctx.Process(target=_train, args=(0, 1, 0, [(0, 512)], q))
-    p.start(); (_, ref), = _collect(q, [p], 1); p.join(timeout=60)
-    port = 29600 + os.getpid() % 1000 + (1 if overlap else 0)
-    procs = [ctx.Process(target=_train, args=(r, 2, port, [(0, 200), (200, 512)], q, overlap)) for r in range(2)]   # unequal shares
-    for p in procs:
-        p.start()
-    got = dict(_collect(q, procs, 2))
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
-    # the replicas apply the same reduced gradient: they must stay bit-identical
-    diverged = [(i, float(np.abs(a - b).max())) for i, (a, b) in enumerate(zip(got[0], got[1])) if not np.array_equal(a, b)]
+def _compare_with_single_process(got, ref, init):
+    # the replicas apply the same reduced gradient: they must stay bit-identical (masters after the gather, and the
+    # bf16 shadow tables every rank's forward actually reads)
+    diverged = [(i, float(np.abs(a - b).max())) for i, (a, b) in enumerate(zip(got[0][0], got[1][0])) if not np.array_equal(a, b)]
+    diverged += [("shadow", i) for i, (a, b) in enumerate(zip(got[0][1], got[1][1])) if not np.array_equal(a, b)]
     print("replica divergence:", diverged)
+    assert got[0][2] == got[1][2] == ref[2], (got[0][2], ref[2])          # per-parameter Adam step counters
     # Against single-process training on the union batch.  Adam (eps = 1e-15) moves an entry by ~lr whatever the size of
     # its gradient, so an entry whose contributions cancel to rounding noise may step the other way: compare the bulk
     # (relative L2 of the difference against the distance trained) and bound the share of such outliers.
     bad = []
-    for i, (a, b, p0) in enumerate(zip(got[0], ref, init)):
+    for i, (a, b, p0) in enumerate(zip(got[0][0], ref[0], init)):
         diff, moved = np.abs(a - b), np.linalg.norm(b - p0)
         rel = np.linalg.norm(a - b) / max(moved, 1e-12)
         outliers = float((diff > 2e-3).mean())
         print(f"param {i}: size {a.size} max diff {diff.max():.3e} rel L2 {rel:.3e} outliers {outliers:.2e}")
-        if not (rel <= 1e-4 and outliers <= 1e-5):      # measured: rel 2e-7 .. 2e-6, no outliers
+        if not (rel <= 1e-4 and outliers <= 1e-5) and moved > 0:      # measured: rel 2e-7 .. 2e-6, no outliers
             bad.append((i, rel, outliers, diff.max()))
     assert not diverged, diverged
     assert not bad, bad
+
+
+def _run_dp_case(cuda, exchange, segs, frame_plan, port_offset):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    init = [p.detach().cpu().numpy() for p in make_model(segs, table_std=0.5, device=cuda)[0].hot_parameters()]
+    p = ctx.Process(target=_train, args=(0, 1, 0, [(0, 512)], q, exchange, segs, frame_plan))
+    p.start(); (_, *ref), = _collect(q, [p], 1); p.join(timeout=60)
+    port = 29600 + os.getpid() % 1000 + port_offset
+    procs = [ctx.Process(target=_train, args=(r, 2, port, [(0, 200), (200, 512)], q, exchange, segs, frame_plan)) for r in range(2)]   # unequal shares
+    for p in procs:
+        p.start()
+    got = {r: rest for r, *rest in _collect(q, procs, 2)}
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    _compare_with_single_process(got, ref, init)
+
+
+@pytest.mark.parametrize("exchange", ["nccl", "p2p"])
+def test_two_rank_dp_equals_single_process(cuda, exchange):
+    """exchange="nccl": one all-reduce of the whole bucket, Adam on every rank; "p2p" (FusedTrainer's default): ONE kernel
+    doing reduce-scatter + rank-sharded Adam + all-gather of the bf16 shadows over NVLink peer memory."""
+    _run_dp_case(cuda, exchange, (6,), None, 1 if exchange == "p2p" else 0)
+
+
+@pytest.mark.parametrize("exchange", ["nccl", "p2p"])
+def test_two_rank_dp_multi_segment(cuda, exchange):
+    """Three temporal segments; steps whose batches touch only some of them: a segment takes part in the step (gradient
+    exchange, Adam, step counter) iff ANY rank's batch touches it -- the union-batch semantics of the reference's
+    optimiser (untouched segments keep .grad = None, trainer.py:174).  DESIGN.md 7.4 of round 1: never run on GPUs."""
+    frames = list(range(15, 15 + 18))
+    plan = [frames[0:3] + frames[12:15], frames[6:9], frames[0:18:3]]       # segments {0,2}, {1}, {0,1,2}
+    assert STEPS == len(plan)
+    _run_dp_case(cuda, exchange, (6, 6, 6), plan, 3 if exchange == "p2p" else 2)
 
 
 def test_tile_sharded_render_equals_monolithic(cuda):

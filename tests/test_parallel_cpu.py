@@ -85,50 +85,28 @@ def test_active_segments_and_gradient_masking():
     assert masked[:5] == grads[:5] and masked[5:10] == [None] * 5 and masked[10:] == grads[10:]
 
 
-def test_trainer_adam_schedule_skips_inactive_segments_and_keeps_their_step_counters():
-    """FusedTrainer.apply_adam's control flow with the kernel call mocked: region waits happen once each and in order,
-    inactive segments are skipped, per-parameter step counters follow torch.optim.Adam's state['step']."""
-    from humanrf_b200.training import FusedTrainer
+def test_optimiser_shards_partition_every_tensor_exactly_once():
+    """FusedTrainer exchange="p2p": rank r owns shard_bounds(n, r, world) of every hash-table tensor (reduce-scatter +
+    sharded Adam + all-gather of the bf16 shadows in hrf_dp_reduce_adam).  The slices must tile [0, n) without overlap,
+    start on the Adam kernel's block boundary, and degrade to empty slices for tensors smaller than the world."""
+    from humanrf_b200.parallel import shard_bounds
 
-    S = 3
-    sizes = [10] * (5 * S) + [3072, 7168]
-
-    class Work:
-        def __init__(self, log, r):
-            self.log, self.r = log, r
-
-        def wait(self):
-            self.log.append(("wait", self.r))
-
-    class Nat:
-        shadows = [[f"shadow{s}{k}" for k in range(4)] for s in range(S)]
-
-        def repack_mlp(self):
-            log.append(("repack",))
-
-    class Model:
-        num_segments = S
-
-    log = []
-    tr = FusedTrainer.__new__(FusedTrainer)
-    tr.slices, tr.regions, tr.adam_order = grid_major_bucket_layout(sizes, S)
-    tr.nat, tr.model, tr.t, tr.steps = Nat(), Model(), 0, [0] * len(sizes)
-    tr.lr, tr.lr_decay, tr.max_steps = 1e-2, 0.5, 100
-    tr._adam = lambda i, shadow, lr, gs: log.append(("adam", i, shadow, tr.steps[i]))
-    tr.apply_adam(0.5, [[Work(log, r)] for r in range(5)], active=[True, False, True])
-    tr.apply_adam(0.5, None, active=[False, True, True])
-    tr.apply_adam(0.5, None, active=None)
-    first = log[:log.index(("repack",))]
-    assert [e for e in first if e[0] == "wait"] == [("wait", r) for r in range(5)]
-    # region k's wait precedes every Adam of region k even when the region's first parameter is inactive
-    for k in range(4):
-        w = first.index(("wait", k))
-        assert all(first.index(e) > w for e in first if e[0] == "adam" and e[1] < 5 * S and e[1] % 5 == k)
-    done = sorted(e[1] for e in first if e[0] == "adam")
-    assert done == [0, 1, 2, 3, 4, 10, 11, 12, 13, 14, 15, 16]                 # segment 1 skipped, MLPs always
-    assert ("adam", 0, "shadow00", 1) in first and ("adam", 4, None, 1) in first   # grids refresh their shadow, vectors do not
-    assert tr.t == 3
-    assert tr.steps == [2] * 5 + [2] * 5 + [3] * 5 + [3, 3]                    # per-parameter counters
+    for n in (0, 1, 4095, 4096, 4097, 7_391_536, 13_969_152, 3 * 4096 * 8, 1_000_003):
+        for world in (1, 2, 3, 4, 8):
+            cover = 0
+            prev_end = 0
+            for r in range(world):
+                a, b = shard_bounds(n, r, world, 4096)
+                assert 0 <= a <= b <= n and a == prev_end if b > a else a <= n
+                if b > a:
+                    assert a % 4096 == 0
+                    cover += b - a
+                    prev_end = b
+            assert cover == n
+            sizes = [shard_bounds(n, r, world, 4096) for r in range(world)]
+            lens = [b - a for a, b in sizes]
+            assert max(lens) - min(l for l in lens if l or True) <= max(lens)      # (monotone non-increasing)
+            assert lens == sorted(lens, reverse=True)
 
 
 def test_allreduce_helpers_are_no_ops_without_a_process_group():

@@ -78,7 +78,7 @@ def test_table_scatter_matches_float64_autograd(cuda, monkeypatch, staged, carry
     sg_dev = torch.from_numpy(np.frombuffer(bytes(sg), dtype=np.uint8).copy()).to(cuda)
     samples = nat.samples_query(pos.to(cuda).contiguous(), None, fr.to(cuda).to(torch.int32).contiguous())
     for first, count in ((0, 1), (1, 3)):                      # split launches, as the data-parallel trainer issues them
-        L.check(L.lib().hrf_field_backward_tables(C.byref(nat.field), C.byref(samples), sg_dev.data_ptr(), None, ws.data_ptr(),
+        L.check(L.lib().hrf_field_backward_tables(C.byref(nat.field), C.byref(samples), sg_dev.data_ptr(), None, None, 0, ws.data_ptr(),
                                                   first, count, L.stream()))
     torch.cuda.synchronize()
     for s in range(m.num_segments):
