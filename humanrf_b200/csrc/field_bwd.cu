@@ -729,6 +729,10 @@ extern "C" int hrf_field_backward_mlp(const hrf_field* f, const hrf_samples* s, 
   return 0;
 }
 
+int hrf_launch_scatter_v2(const hrf_field* f, const hrf_samples* s, const hrf_segment_grads* seg_grads, const void* grid_feat_bf16,
+                          const int32_t* feat_index, int64_t grid_feat_stride, const void* workspace, int grid_first, int grid_count,
+                          cudaStream_t st);   // scatter_v2.cu
+
 extern "C" int hrf_field_backward_tables(const hrf_field* f, const hrf_samples* s, const hrf_segment_grads* seg_grads,
                                          const void* grid_feat_bf16, const int32_t* feat_index, int64_t grid_feat_stride,
                                          const void* workspace, int grid_first, int grid_count, void* stream) {
@@ -736,6 +740,11 @@ extern "C" int hrf_field_backward_tables(const hrf_field* f, const hrf_samples* 
   HRF_REQUIRE(grid_first >= 0 && grid_count >= 1 && grid_first + grid_count <= 4, "grids are 0..3 (xyz, xyt, yzt, xzt)");
   if (s->num_samples == 0) return 0;
   HRF_REQUIRE(workspace != nullptr, "needs the workspace hrf_field_backward_mlp filled");
+  // HRF_SCATTER_V2=0 selects the first-generation kernels below (kept for A/B and as a cross-check in the tests)
+  const bool v2 = [] { const char* e = getenv("HRF_SCATTER_V2"); return !(e && e[0] == '0'); }();   // (read per call: the tests switch it)
+  if (v2)
+    return hrf_launch_scatter_v2(f, s, seg_grads, grid_feat_bf16, feat_index, grid_feat_stride, workspace, grid_first, grid_count,
+                                 reinterpret_cast<cudaStream_t>(stream));
   ScatterArgs sa;
   sa.f = *f;
   sa.s = *s;

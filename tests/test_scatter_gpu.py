@@ -23,12 +23,20 @@ def _relnorm(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
-@pytest.mark.parametrize("staged,carry,chunk,taps", [("1", "1", "8", "0"), ("1", "1", "8", "1"), ("1", "0", "8", "1"), ("0", "1", "16", "0"),
-                                                     ("0", "0", "8", "0"), ("0", "1", "5", "0")],
-                         ids=["staged", "staged-tapstage", "staged-tapstage-nocarry", "strided16", "strided8-nocarry", "strided5"])
+@pytest.mark.parametrize("staged,carry,chunk,taps", [("v2", "6", "", ""), ("v2", "5", "", ""), ("1", "1", "8", "0"), ("1", "1", "8", "1"),
+                                                     ("1", "0", "8", "1"), ("0", "1", "16", "0"), ("0", "0", "8", "0"), ("0", "1", "5", "0")],
+                         ids=["v2-parity-slots", "v2-5ctas", "staged", "staged-tapstage", "staged-tapstage-nocarry", "strided16",
+                              "strided8-nocarry", "strided5"])
 def test_table_scatter_matches_float64_autograd(cuda, monkeypatch, staged, carry, chunk, taps):
-    """staged = the default kernel (shared-memory staging, 8 samples per thread); strided = the first kernel, kept
-    behind HRF_SCATTER_STAGED=0."""
+    """v2 = the default kernel (csrc/scatter_v2.cu: parity-slot accumulators, straight-line step); staged / strided = the
+    first-generation kernels kept behind HRF_SCATTER_V2=0 (shared-memory staging with the shifted-corner carry; the
+    strided first kernel behind HRF_SCATTER_STAGED=0)."""
+    if staged == "v2":
+        monkeypatch.setenv("HRF_SCATTER_V2", "1")
+        monkeypatch.setenv("HRF_SCATTER_CTAS", carry)
+        staged, carry, chunk, taps = "1", "1", "8", "0"
+    else:
+        monkeypatch.setenv("HRF_SCATTER_V2", "0")
     monkeypatch.setenv("HRF_SCATTER_STAGED", staged)
     monkeypatch.setenv("HRF_SCATTER_TAPSTAGE", taps)
     monkeypatch.setenv("HRF_SCATTER_CARRY", carry)
@@ -77,7 +85,7 @@ def test_table_scatter_matches_float64_autograd(cuda, monkeypatch, staged, carry
         sg[s].vectors = grads[5 * s + 4].data_ptr()
     sg_dev = torch.from_numpy(np.frombuffer(bytes(sg), dtype=np.uint8).copy()).to(cuda)
     samples = nat.samples_query(pos.to(cuda).contiguous(), None, fr.to(cuda).to(torch.int32).contiguous())
-    for first, count in ((0, 1), (1, 3)):                      # split launches, as the data-parallel trainer issues them
+    for first, count in ((0, 1), (1, 3)):                      # split launches (per-table schedule)
         L.check(L.lib().hrf_field_backward_tables(C.byref(nat.field), C.byref(samples), sg_dev.data_ptr(), None, None, 0, ws.data_ptr(),
                                                   first, count, L.stream()))
     torch.cuda.synchronize()
