@@ -41,10 +41,21 @@ struct EarlyStop {
   float step, stop_depth;
 };
 
+// Optional compositing epilogue of the forward kernel (inference): see field_fwd.cu.
+struct Composite {
+  const int32_t* ray_offsets;   // [R+1] first sample of each ray (samples sorted by ray); NULL disables the epilogue
+  const float* background;      // [R,3] or NULL
+  float* color;                 // [R,3]
+  float* wsum;                  // [R]
+  float* partial;               // [tiles][2][8]: (optical depth, C.r, C.g, C.b, W) of the ray segments cut by a tile border
+  float step;
+};
+
 struct FieldArgs {
   hrf_field f;
   hrf_samples s;
   EarlyStop es;
+  Composite comp;
   float* sigma;
   uint32_t* geo;   // bf16 [N,16] viewed as u32 pairs
   float* rgb;

@@ -103,7 +103,13 @@ __device__ __forceinline__ void store_hidden(unsigned char* hbuf, int row, const
 
 // kFromFeat: the composed features come from an earlier pass (args.feat_in, optionally through args.feat_index) and the
 // encode is skipped: the MLP half of the kernel alone (render pass of the survivors of prune_samples).
-template <bool kSimt, int kCtasPerSm, bool kSaveGrid = false, int kLevelUnroll = 4, bool kFromFeat = false>
+// kComposite: the per-ray compositing of humanrf/volume_rendering.py:123-145 (nerfacc render_weight_from_density +
+// accumulate_along_rays + background blend) runs as the epilogue of the tile: sigma / rgb never go to HBM.  Samples are
+// sorted by ray, so a tile holds a run of whole rays plus at most one ray cut by its first border and one cut by its
+// last: whole rays are finished here; the (at most two) cut segments leave a 5-float partial
+// (optical depth, transmittance-weighted colour and weight relative to the segment start) that composite_fixup_kernel
+// chains in tile order.  Segmented warp-shuffle scans keyed by the ray index; warps are joined through 3 words of smem.
+template <bool kSimt, int kCtasPerSm, bool kSaveGrid = false, int kLevelUnroll = 4, bool kFromFeat = false, bool kComposite = false>
 __global__ void __launch_bounds__(kTile, kCtasPerSm) field_forward_kernel(const __grid_constant__ FieldArgs args) {
   extern __shared__ unsigned char smem_raw[];
   FwdSmem& sm = *reinterpret_cast<FwdSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
@@ -236,11 +242,71 @@ __global__ void __launch_bounds__(kTile, kCtasPerSm) field_forward_kernel(const 
     run_layer<kSimt, 64, 64>(sm, sm.a, w_col2(f.color_in_width), phase, v);
     store_hidden(sm.a, tid, v);
     run_layer<kSimt, 16, 64>(sm, sm.a, w_col3(f.color_in_width), phase, o);
+    const float c0 = 1.f / (1.f + __expf(-o[0])), c1 = 1.f / (1.f + __expf(-o[1])), c2 = 1.f / (1.f + __expf(-o[2]));
     if (valid && args.rgb != nullptr) {
       float* rp = args.rgb + 3 * i;
-      rp[0] = 1.f / (1.f + __expf(-o[0]));
-      rp[1] = 1.f / (1.f + __expf(-o[1]));
-      rp[2] = 1.f / (1.f + __expf(-o[2]));
+      rp[0] = c0, rp[1] = c1, rp[2] = c2;
+    }
+    if constexpr (kComposite) {
+      // The activation tile is free (the last MMA that read it has committed): its first bytes join the four warps.
+      int* x_first = reinterpret_cast<int*>(sm.a);          // [4] ray of lane 0
+      int* x_last = x_first + 4;                            // [4] ray of lane 31
+      float* x_tail = reinterpret_cast<float*>(x_first + 8);  // [4][5] inclusive sums of the warp's last ray at lane 31
+      const int lane = tid & 31, warp = tid >> 5;
+      const int ray = valid ? (int)__ldg(args.s.ray_indices + i) : -1;
+      float sdt = 0.f;
+      if (valid) {
+        const float t = __ldg(args.s.sample_distances + i);
+        sdt = sigma * __fsub_rn(__fadd_rn(t, args.comp.step), t);   // sigmas * (t_ends - t_starts), volume_rendering.py:124-129
+      }
+      auto seg_scan = [&](float v) {   // inclusive sum over the lanes of this warp that carry the same ray
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const float u = __shfl_up_sync(0xffffffffu, v, d);
+          const int ru = __shfl_up_sync(0xffffffffu, ray, d);
+          if (lane >= d && ru == ray) v += u;
+        }
+        return v;
+      };
+      auto carry_in = [&](int k) {   // what the earlier warps of the tile hold for this thread's ray
+        float c = 0.f;
+        for (int w = warp - 1; w >= 0; --w) {
+          if (x_last[w] != ray) break;
+          c += x_tail[w * 5 + k];
+          if (x_first[w] != ray) break;
+        }
+        return c;
+      };
+      float depth = seg_scan(sdt);
+      __syncthreads();   // every thread is done with the tile's operands
+      if (lane == 0) x_first[warp] = ray;
+      if (lane == 31) x_last[warp] = ray, x_tail[warp * 5] = depth;
+      __syncthreads();
+      depth += carry_in(0);
+      const float wgt = valid ? __expf(-(depth - sdt)) * (1.f - __expf(-sdt)) : 0.f;
+      float a0 = seg_scan(wgt * c0), a1 = seg_scan(wgt * c1), a2 = seg_scan(wgt * c2), a3 = seg_scan(wgt);
+      if (lane == 31) x_tail[warp * 5 + 1] = a0, x_tail[warp * 5 + 2] = a1, x_tail[warp * 5 + 3] = a2, x_tail[warp * 5 + 4] = a3;
+      __syncthreads();
+      a0 += carry_in(1), a1 += carry_in(2), a2 += carry_in(3), a3 += carry_in(4);
+      int ray_next = __shfl_down_sync(0xffffffffu, ray, 1);
+      if (lane == 31) ray_next = warp < 3 ? x_first[warp + 1] : -2;
+      if (valid && ray_next != ray) {   // last sample of this ray inside the tile
+        const int64_t tile_start = i - tid;
+        const int b = __ldg(args.comp.ray_offsets + ray), e = __ldg(args.comp.ray_offsets + ray + 1);
+        if (b >= tile_start && e <= tile_start + kTile) {   // the whole ray lives in this tile
+          const float k = 1.f - a3;
+          const float* bg = args.comp.background;
+          float* cp = args.comp.color + 3 * (int64_t)ray;
+          cp[0] = a0 + (bg != nullptr ? bg[3 * ray] * k : 0.f);
+          cp[1] = a1 + (bg != nullptr ? bg[3 * ray + 1] * k : 0.f);
+          cp[2] = a2 + (bg != nullptr ? bg[3 * ray + 2] * k : 0.f);
+          args.comp.wsum[ray] = a3;
+        } else {
+          float* pp = args.comp.partial + ((tile_start / kTile) * 2 + (b < tile_start ? 0 : 1)) * 8;
+          pp[0] = depth, pp[1] = a0, pp[2] = a1, pp[3] = a2, pp[4] = a3;
+        }
+      }
+      __syncthreads();   // the scratch words are overwritten by the next tile's operands
     }
   }
 
@@ -283,7 +349,9 @@ static int launch_field_forward(const FieldArgs& a, int mlp_impl, cudaStream_t s
   // the limiter.  Default 1.
   static const int unroll = [] { const char* e = getenv("HRF_FWD_UNROLL"); const int v = e ? atoi(e) : 1; return (v == 2 || v == 4) ? v : 1; }();
   int rc;
-  if (a.feat_in != nullptr) rc = launch(field_forward_kernel<false, 5, false, 1, true>);
+  if (a.comp.ray_offsets != nullptr && a.feat_in != nullptr) rc = launch(field_forward_kernel<false, 5, false, 1, true, true>);
+  else if (a.comp.ray_offsets != nullptr) rc = launch(field_forward_kernel<false, 5, false, 1, false, true>);
+  else if (a.feat_in != nullptr) rc = launch(field_forward_kernel<false, 5, false, 1, true>);
   else if (mlp_impl != 0) rc = launch(field_forward_kernel<true, 4>);
   else if (a.egrid != nullptr && unroll == 2) rc = launch(field_forward_kernel<false, 5, true, 2>);
   else if (a.egrid != nullptr && unroll == 1) rc = launch(field_forward_kernel<false, 5, true, 1>);
@@ -326,6 +394,7 @@ extern "C" int hrf_field_forward(const hrf_field* f, const hrf_samples* s, int m
   a.f = *f;
   a.s = *s;
   a.es = EarlyStop{};
+  a.comp = Composite{};
   a.sigma = sigma;
   a.geo = reinterpret_cast<uint32_t*>(geo_bf16);
   a.rgb = rgb;
@@ -347,6 +416,7 @@ extern "C" int hrf_field_forward_from_features(const hrf_field* f, const hrf_sam
   a.f = *f;
   a.s = *s;
   a.es = EarlyStop{};
+  a.comp = Composite{};
   a.sigma = sigma;
   a.geo = nullptr;
   a.rgb = rgb;
@@ -369,6 +439,67 @@ __global__ void ray_max_chunks_kernel(const int32_t* __restrict__ off, int64_t n
 }
 }  // namespace hrf
 
+namespace hrf {
+// Rays whose samples straddle tile borders: chain the per-tile partials front to back.  Rays without samples are pure
+// background (volume_rendering.py:144-145 with weights_sum = 0).  One thread per ray.
+__global__ void __launch_bounds__(256) composite_fixup_kernel(const Composite c, int64_t num_rays) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= num_rays) return;
+  const int b = c.ray_offsets[r], e = c.ray_offsets[r + 1];
+  float col0 = 0.f, col1 = 0.f, col2 = 0.f, w = 0.f;
+  if (e > b) {
+    const int tf = b / kTile, tl = (e - 1) / kTile;
+    if (tf == tl) return;   // finished by the forward kernel
+    float depth = 0.f;
+    for (int t = tf; t <= tl; ++t) {
+      const float* pp = c.partial + ((int64_t)t * 2 + (t == tf ? 1 : 0)) * 8;
+      const float T = __expf(-depth);
+      col0 += T * pp[1], col1 += T * pp[2], col2 += T * pp[3], w += T * pp[4];
+      depth += pp[0];
+    }
+  }
+  const float k = 1.f - w;
+  if (c.background != nullptr) col0 += c.background[3 * r] * k, col1 += c.background[3 * r + 1] * k, col2 += c.background[3 * r + 2] * k;
+  c.color[3 * r] = col0, c.color[3 * r + 1] = col1, c.color[3 * r + 2] = col2;
+  c.wsum[r] = w;
+}
+}  // namespace hrf
+
+extern "C" int64_t hrf_render_fused_workspace_bytes(int64_t num_samples_capacity) {
+  return ((num_samples_capacity + kTile - 1) / kTile) * 2 * 8 * (int64_t)sizeof(float) + 64;
+}
+
+extern "C" int hrf_render_fused(const hrf_field* f, const hrf_samples* s, const int32_t* ray_offsets, int64_t num_rays, float step,
+                                const float* background, const void* feat_in_bf16, const int32_t* feat_index, float* color,
+                                float* weights_sum, void* workspace, void* stream) {
+  if (int rc = check_field_args(f, s, 1)) return rc;
+  HRF_REQUIRE(ray_offsets != nullptr && color != nullptr && weights_sum != nullptr, "null argument");
+  HRF_REQUIRE(s->ray_origins != nullptr, "hrf_render_fused needs the ray-batch form (samples sorted by ray)");
+  HRF_REQUIRE(s->num_samples < (1ll << 31) && num_rays < (1ll << 31), "more than 2^31 samples / rays per call is not supported");
+  if (num_rays == 0) return 0;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  Composite c;
+  c.ray_offsets = ray_offsets, c.background = background, c.color = color, c.wsum = weights_sum;
+  c.partial = reinterpret_cast<float*>(workspace), c.step = step;
+  if (s->num_samples > 0) {
+    HRF_REQUIRE(workspace != nullptr, "null workspace");
+    FieldArgs a;
+    a.f = *f;
+    a.s = *s;
+    a.es = EarlyStop{};
+  a.comp = Composite{};
+    a.comp = c;
+    a.sigma = nullptr, a.geo = nullptr, a.rgb = nullptr, a.feat = nullptr, a.egrid = nullptr;
+    a.feat_in = reinterpret_cast<const uint4*>(feat_in_bf16);
+    a.feat_index = feat_in_bf16 != nullptr ? feat_index : nullptr;
+    a.mode = 1;
+    if (int rc = launch_field_forward(a, 0, st, s->num_samples_dev != nullptr)) return rc;
+  }
+  composite_fixup_kernel<<<(unsigned)((num_rays + 255) / 256), 256, 0, st>>>(c, num_rays);
+  HRF_CHECK_LAUNCH();
+  return 0;
+}
+
 extern "C" int64_t hrf_density_early_stop_workspace_bytes(int64_t num_rays) { return 4 * num_rays + 64; }
 
 extern "C" int hrf_field_density_early_stop(const hrf_field* f, const hrf_samples* s, const int32_t* ray_offsets,
@@ -385,6 +516,7 @@ extern "C" int hrf_field_density_early_stop(const hrf_field* f, const hrf_sample
   FieldArgs a;
   a.f = *f;
   a.s = *s;
+  a.comp = Composite{};
   a.es.ray_offsets = ray_offsets;
   a.es.num_rays = num_rays;
   a.es.ray_depth = reinterpret_cast<float*>(ws + 64);

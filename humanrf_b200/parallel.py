@@ -142,41 +142,67 @@ def broadcast_parameters_(params, src: int = 0, group=None, model=None) -> None:
 class TileShardedRenderer:
     """Full-image rendering with the image's pixels split into contiguous ranges over the ranks
     (Trainer.test / validate, trainer.py:258-526, without the per-batch D2H and the CPU scatter: the image is
-    assembled on the device)."""
+    assembled on the device).
 
-    def __init__(self, model, occupancy_grid, rays_per_batch: int = 16384, step: float = 4e-4):
+    Per batch of `rays_per_batch` pixels: sampler -> density pass with the exact early stop (keeps the composed features of
+    every candidate it evaluates) -> visibility compaction -> ONE fused kernel for the survivors (MLPs on the kept
+    features + compositing, hrf_render_fused) -> colours placed by the ray mask.  The only host read is the sampler's
+    pair of counters that sizes the candidate arrays: the survivor count stays on the device, the placement is a
+    cumulative-sum gather (no nonzero())."""
+
+    def __init__(self, model, occupancy_grid, rays_per_batch: int = 262144, step: float = 4e-4):
         self.model, self.og, self.rays_per_batch, self.step = model, occupancy_grid, rays_per_batch, step
+        self.last_stats = {}
 
     @torch.no_grad()
     def render_range(self, cam: dict, start: int, end: int, background: float = 0.0) -> torch.Tensor:
         """cam: dict of the per-image sampler tables for ONE image (frame_numbers, camera_numbers, grid handle,
         landscape, inverse_krs, camera_origins, aabb, G, width, height).  Returns float32 [end-start, 3]."""
+        import ctypes as C
+
+        from . import _lib as L
         from .dataset import ray_sampler_native as rs
-        from .dataset.input_batch import InputBatch
-        from .volume_rendering import prune_samples, render
+        from .volume_rendering import ray_offsets, render_fused
 
         dev = cam["aabb"].device
-        out = torch.full((end - start, 3), float(background), dtype=torch.float32, device=dev)
+        lib, nat, step = L.lib(), self.model.native(), self.step
+        parts = []
         empty_rgba = torch.zeros((0, 4), dtype=torch.uint8, device=dev)
         empty_mask = torch.zeros(0, dtype=torch.bool, device=dev)
+        candidates = 0
         for s in range(start, end, self.rays_per_batch):
             e = min(s + self.rays_per_batch, end)
             idx = torch.arange(s, e, dtype=torch.int64, device=dev)
             (o, d, _, fn, cn, mm, mask, dist_, rel) = rs.get_samples_occupancy_minmax(
                 empty_rgba, empty_mask, cam["frame_numbers"], cam["camera_numbers"], cam["grid_handles"],
                 cam["landscape"], idx, cam["inverse_krs"], cam["camera_origins"], cam["aabb"], cam["G"], cam["width"],
-                cam["height"], self.step, False)
-            if o.shape[0] == 0:
+                cam["height"], step, False)
+            nr, n = o.shape[0], dist_.shape[0]
+            candidates += n
+            if nr == 0:
+                parts.append(torch.full((e - s, 3), float(background), dtype=torch.float32, device=dev))
                 continue
-            ib = InputBatch(ray_origins=o, ray_directions=d, minmaxes=mm, ray_masks=mask.view(-1, 1),
-                            frame_numbers=fn.view(-1, 1), camera_numbers=cn.view(-1, 1),
-                            sample_distances=dist_.view(-1, 1), ray_indices=rel.long(), width=cam["width"],
-                            height=cam["height"])
-            prune_samples(ib, self.model, is_training=False, render_step_size=self.step)
-            bg = torch.full((o.shape[0], 3), float(background), dtype=torch.float32, device=dev)
-            ro = render(ib, self.model, bg, is_training=False, render_step_size=self.step)
-            out[(s - start) + torch.nonzero(mask).view(-1)] = ro.color        # combine_rays_to_image, on device
-        return out
+            ri = rel.long()
+            off0 = ray_offsets(ri, nr)
+            samples = nat.samples_rays(o, d, fn, dist_, ri)
+            sigma, saved = nat.density_early_stop(samples, off0, nr, step, save="feat")
+            keep = torch.empty(n, dtype=torch.uint8, device=dev)
+            kept_off = torch.empty(nr + 1, dtype=torch.int32, device=dev)
+            t2 = torch.empty(n, dtype=torch.float32, device=dev)
+            ri2 = torch.empty(n, dtype=torch.int64, device=dev)
+            src = torch.empty(n, dtype=torch.int32, device=dev)
+            count = torch.zeros(1, dtype=torch.int64, device=dev)
+            L.check(lib.hrf_prune(sigma.data_ptr(), dist_.data_ptr(), ri.data_ptr(), off0.data_ptr(), nr, step, 1e-4, 1e-4,
+                                  keep.data_ptr(), kept_off.data_ptr(), t2.data_ptr(), ri2.data_ptr(), src.data_ptr(),
+                                  count.data_ptr(), L.stream()))
+            color, _ = render_fused(self.model, o, d, fn, t2, ri2, nr, float(background), step, reuse=(saved, src, kept_off),
+                                    count_dev=count)
+            # combine_rays_to_image (volume_rendering.py:26-39) on the device, without nonzero(): ray j of the compacted
+            # batch is the (j+1)-th set bit of the mask
+            pos = (torch.cumsum(mask.view(-1).long(), 0) - 1).clamp_(min=0)
+            parts.append(torch.where(mask.view(-1, 1), color[pos], torch.full((1, 3), float(background), device=dev)))
+        self.last_stats = {"candidate_samples": candidates}
+        return parts[0] if len(parts) == 1 else torch.cat(parts, 0)
 
     def render_image_sharded(self, cam: dict, rank: int, world: int, background: float = 0.0):
         """This rank's tile of the image: returns (start, end, colours)."""

@@ -382,7 +382,7 @@ class _NativeField:
         return sigma if save == "none" else (sigma, saved)
 
     def backward(self, samples: L.Samples, d_sigma, d_rgb, feat, grad_tensors: List[torch.Tensor], per_table: bool = False,
-                 d_geo=None):
+                 d_geo=None, feat_index=None):
         """grad_tensors: fp32 buffers in hot_parameters() order (accumulated into).  per_table launches the scatter once
         per grid instead of once for all four.  d_geo: fp32 [N,15] gradient of the geometry features, or None."""
         m = self.model
@@ -400,17 +400,18 @@ class _NativeField:
         d_emb = grad_tensors[i + 2] if m.camera_embedding_dim > 0 else None
         ws = torch.empty(int(samples.num_samples) * 40, dtype=torch.float32, device=dev)   # 160 B / sample
         n = int(samples.num_samples)
-        egrid = feat.data_ptr() + 64 * n if (feat is not None and feat.numel() >= n * 160 and n > 0) else None
+        # `feat` with a row index = composed features of a pruning pass (no per-grid features: the scatter re-gathers)
+        egrid = feat.data_ptr() + 64 * n if (feat is not None and feat_index is None and feat.numel() >= n * 160 and n > 0) else None
         if per_table:
             L.check(L.lib().hrf_field_backward_mlp(C.byref(self.field), C.byref(samples), L.ptr(d_sigma), L.ptr(d_rgb),
-                                                   L.ptr(d_geo), L.ptr(feat), None, d_mlp.data_ptr(), L.ptr(d_emb),
+                                                   L.ptr(d_geo), L.ptr(feat), L.ptr(feat_index), d_mlp.data_ptr(), L.ptr(d_emb),
                                                    ws.data_ptr(), L.stream()))
             for k in range(4):
                 L.check(L.lib().hrf_field_backward_tables(C.byref(self.field), C.byref(samples), sg_dev.data_ptr(), egrid,
                                                           None, 0, ws.data_ptr(), k, 1, L.stream()))
         else:
             L.check(L.lib().hrf_field_backward(C.byref(self.field), C.byref(samples), sg_dev.data_ptr(), L.ptr(d_sigma),
-                                               L.ptr(d_rgb), L.ptr(d_geo), L.ptr(feat), egrid, None, 0, d_mlp.data_ptr(),
+                                               L.ptr(d_rgb), L.ptr(d_geo), L.ptr(feat), egrid, L.ptr(feat_index), 0, d_mlp.data_ptr(),
                                                L.ptr(d_emb), ws.data_ptr(), L.stream()))
         grad_tensors[i].add_(d_mlp[:MLP_SIGMA_PARAMS])
         grad_tensors[i + 1].add_(d_mlp[MLP_SIGMA_PARAMS:])

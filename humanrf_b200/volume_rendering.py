@@ -7,7 +7,11 @@ returns None) and ``render`` with the reference signatures.  Differences by desi
   reads ``sample_distances`` + ``ray_indices`` and the per-ray arrays directly (the reference
   builds three [N,3] gathers per call, volume_rendering.py:66-72,110-119);
 * nerfacc's scan-by-key / scatter-add are replaced by one warp-per-ray kernel
-  (csrc/composite.cu); pruning compacts on the device and reads back one counter.
+  (csrc/composite.cu); pruning compacts on the device and reads back one counter;
+* without gradients ``render`` is ONE field kernel with the compositing as its epilogue (hrf_render_fused): per-sample
+  sigma / rgb never reach HBM;
+* ``prune_samples`` keeps the composed features of the candidates it encoded (64 B/sample) on the batch object; a
+  following ``render`` of the same (unchanged) batch runs the two MLPs on them instead of encoding the survivors again.
 """
 from __future__ import annotations
 
@@ -69,50 +73,63 @@ def prune_samples(input_batch: InputBatch, scene_representation: HumanRF, is_tra
     dev = t.device
     off = ray_offsets(ri, num_rays)
     # density-only pass; chunks of a ray behind an already opaque prefix are provably pruned and are not evaluated
-    sigma = nat.density_early_stop(nat.samples_rays(o, d, fr, t, ri), off, num_rays, render_step_size)
+    sigma, saved = nat.density_early_stop(nat.samples_rays(o, d, fr, t, ri), off, num_rays, render_step_size, save="feat")
     keep = torch.empty(n, dtype=torch.uint8, device=dev)
     kept_off = torch.empty(num_rays + 1, dtype=torch.int32, device=dev)
     out_t = torch.empty(n, dtype=torch.float32, device=dev)
     out_ri = torch.empty(n, dtype=torch.int64, device=dev)
+    src = torch.empty(n, dtype=torch.int32, device=dev)
     counter = torch.zeros(1, dtype=torch.int64, device=dev)
     L.check(L.lib().hrf_prune(sigma.data_ptr(), t.data_ptr(), ri.data_ptr(), off.data_ptr(), num_rays,
                               float(render_step_size), 1e-4, 1e-4, keep.data_ptr(), kept_off.data_ptr(),
-                              out_t.data_ptr(), out_ri.data_ptr(), None, counter.data_ptr(), L.stream()))
-    kept = int(counter.item())
+                              out_t.data_ptr(), out_ri.data_ptr(), src.data_ptr(), counter.data_ptr(), L.stream()))
+    kept = int(counter.item())      # the reference's API hands out exactly-sized tensors (merge_input_batches concatenates them)
     ib.sample_distances = out_t[:kept].view(-1, 1)
     ib.ray_indices = out_ri[:kept]
+    # what a render() of this very batch can reuse: composed features of the candidates, the survivors' rows in them, the
+    # survivors' ray-offset table.  Tied to the identity of the two tensors above: any edit of the batch drops it.
+    ib._hrf_reuse = (saved, src[:kept], kept_off, ib.sample_distances, ib.ray_indices, id(scene_representation))
+
+
+def _reusable_features(ib: InputBatch, model: HumanRF):
+    r = getattr(ib, "_hrf_reuse", None)
+    if r is None or r[3] is not ib.sample_distances or r[4] is not ib.ray_indices or r[5] != id(model):
+        return None
+    return r[0], r[1], r[2]
 
 
 class _RenderFunction(torch.autograd.Function):
     """field forward (ray-batch form) + compositing; backward = composite bwd + fused field bwd."""
 
     @staticmethod
-    def forward(ctx, model: HumanRF, o, d, fr, t, ri, num_rays, background, step, cams, needs_grad, active, *params):
+    def forward(ctx, model: HumanRF, o, d, fr, t, ri, num_rays, background, step, cams, needs_grad, active, reuse, *params):
         nat = model.native()
         dev = t.device
         samples = nat.samples_rays(o, d, fr, t, ri, cams)
-        sigma, _, rgb, feat = nat.forward(samples, 1, want_geo=False, want_feat=needs_grad)
-        off = ray_offsets(ri, num_rays)
+        src = None
+        if reuse is not None:       # composed features of the prune pass: MLPs only, and the scatter re-gathers the tables
+            feat, src, off = reuse
+            sigma, rgb = nat.forward_from_features(samples, feat, src)
+        else:
+            sigma, _, rgb, feat = nat.forward(samples, 1, want_geo=False, want_feat=needs_grad)
+            off = ray_offsets(ri, num_rays)
         color = torch.empty((num_rays, 3), dtype=torch.float32, device=dev)
         wsum = torch.empty((num_rays, 1), dtype=torch.float32, device=dev)
-        bg = None
-        if background is not None:
-            bg = torch.as_tensor(background, dtype=torch.float32, device=dev)
-            bg = bg.expand(num_rays, 3).contiguous() if bg.dim() < 2 or bg.shape[0] != num_rays else bg.contiguous()
+        bg = _background_rows(background, num_rays, dev)
         L.check(L.lib().hrf_composite_forward(sigma.data_ptr(), rgb.data_ptr(), t.data_ptr(), off.data_ptr(), num_rays,
                                               float(step), L.ptr(bg), color.data_ptr(), wsum.data_ptr(), None,
                                               L.stream()))
         ctx.model, ctx.num_rays, ctx.step, ctx.active = model, num_rays, float(step), active
         ctx.bg = bg
         ctx.save_for_backward(o, d, fr, t, ri, sigma, rgb, off, feat if feat is not None else t,
-                              cams if cams is not None else fr)
-        ctx.has_cams = cams is not None
+                              cams if cams is not None else fr, src if src is not None else fr)
+        ctx.has_cams, ctx.has_src = cams is not None, src is not None
         return color, wsum
 
     @staticmethod
     def backward(ctx, d_color, d_wsum):
         model = ctx.model
-        o, d, fr, t, ri, sigma, rgb, off, feat, cams = ctx.saved_tensors
+        o, d, fr, t, ri, sigma, rgb, off, feat, cams, src = ctx.saved_tensors
         nat = model.native()
         dev = t.device
         n = t.shape[0]
@@ -125,12 +142,13 @@ class _RenderFunction(torch.autograd.Function):
                                                d_sigma.data_ptr(), d_rgb.data_ptr(), L.stream()))
         params = model.hot_parameters()
         grads = [torch.zeros_like(p) for p in params]
-        nat.backward(nat.samples_rays(o, d, fr, t, ri, cams if ctx.has_cams else None), d_sigma, d_rgb, feat, grads)
+        nat.backward(nat.samples_rays(o, d, fr, t, ri, cams if ctx.has_cams else None), d_sigma, d_rgb, feat, grads,
+                     feat_index=src if ctx.has_src else None)
         if ctx.active is not None:      # segments the batch did not touch get no gradient at all (None), as in the reference
             from .parallel import mask_inactive_segment_grads
 
             grads = mask_inactive_segment_grads(grads, ctx.active)
-        return (None,) * 12 + tuple(grads)
+        return (None,) * 13 + tuple(grads)
 
 
 def render(input_batch: InputBatch, scene_representation: HumanRF, background_rgb: torch.Tensor, is_training: bool,
@@ -144,8 +162,45 @@ def render(input_batch: InputBatch, scene_representation: HumanRF, background_rg
     params = scene_representation.hot_parameters()
     # (ctx.needs_input_grad ignores torch.no_grad(): decide here whether the backward buffers are worth saving)
     needs_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    reuse = _reusable_features(ib, scene_representation)
+    if not needs_grad:
+        color, wsum = render_fused(scene_representation, o, d, fr, t, ri, ib.num_rays, background_rgb, render_step_size, cams,
+                                   reuse=reuse)
+        return RenderOutput(color=color, weights_sum=wsum)
     # humanrf.py:162-179: only the segments of this batch's frames are run (and receive gradients)
-    active = scene_representation.active_segment_list(fr, ib.unique_frame_numbers) if needs_grad else None
+    active = scene_representation.active_segment_list(fr, ib.unique_frame_numbers)
     color, wsum = _RenderFunction.apply(scene_representation, o, d, fr, t, ri, ib.num_rays, background_rgb,
-                                        render_step_size, cams, needs_grad, active, *params)
+                                        render_step_size, cams, needs_grad, active, reuse, *params)
     return RenderOutput(color=color, weights_sum=wsum)
+
+
+def _background_rows(background, num_rays: int, dev) -> "torch.Tensor | None":
+    if background is None:
+        return None
+    bg = torch.as_tensor(background, dtype=torch.float32, device=dev)
+    return bg.expand(num_rays, 3).contiguous() if bg.dim() < 2 or bg.shape[0] != num_rays else bg.contiguous()
+
+
+@torch.no_grad()
+def render_fused(model: HumanRF, o, d, fr, t, ri, num_rays: int, background, step: float = 4e-4, cams=None, reuse=None,
+                 count_dev=None, ray_offsets_dev=None):
+    """Inference render of a ray batch in one field kernel (hrf_render_fused): encode -> MLPs -> compositing, nothing per
+    sample written to HBM.  reuse = (features [M,32] bf16, row index per sample, ray-offset table) from a pruning pass:
+    no encode at all.  count_dev: live sample count on the device (t / ri are then capacity-sized).
+    Returns (color [R,3], weights_sum [R,1])."""
+    nat = model.native()
+    dev = t.device
+    lib = L.lib()
+    samples = nat.samples_rays(o, d, fr, t, ri, cams, count_dev=count_dev)
+    feat = src = None
+    if reuse is not None:
+        feat, src, off = reuse
+    else:
+        off = ray_offsets_dev if ray_offsets_dev is not None else ray_offsets(ri, num_rays)
+    color = torch.empty((num_rays, 3), dtype=torch.float32, device=dev)
+    wsum = torch.empty((num_rays, 1), dtype=torch.float32, device=dev)
+    bg = _background_rows(background, num_rays, dev)
+    ws = torch.empty(int(lib.hrf_render_fused_workspace_bytes(t.shape[0])), dtype=torch.uint8, device=dev)
+    L.check(lib.hrf_render_fused(C.byref(nat.field), C.byref(samples), off.data_ptr(), num_rays, float(step), L.ptr(bg),
+                                 L.ptr(feat), L.ptr(src), color.data_ptr(), wsum.data_ptr(), ws.data_ptr(), L.stream()))
+    return color, wsum

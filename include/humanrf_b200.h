@@ -166,6 +166,19 @@ int hrf_field_forward_from_features(const hrf_field* f, const hrf_samples* s, co
                                     const int32_t* feat_index, float* sigma /* [N] */, float* rgb /* [N,3] */,
                                     void* stream);
 
+/* Inference render in ONE field kernel (humanrf/volume_rendering.py:87-150 without gradients): encode -> sigma MLP ->
+ * colour MLP -> per-ray compositing, w_i = exp(-sum_{j<i} sigma_j dt_j) (1 - exp(-sigma_i dt_i)), colour = sum w rgb +
+ * background (1 - sum w).  Per-sample sigma / rgb never leave the SM; a small second kernel chains the rays that
+ * straddle 128-sample tile borders and writes the background for rays without samples.  Samples must be sorted by
+ * ray (ray_offsets[r] = first sample of ray r).  feat_in / feat_index: optional composed features of an earlier
+ * pass (hrf_field_forward_from_features semantics; then nothing is encoded here).  s->num_samples_dev is honoured.
+ * workspace: hrf_render_fused_workspace_bytes(s->num_samples) bytes of device scratch. */
+int64_t hrf_render_fused_workspace_bytes(int64_t num_samples_capacity);
+int hrf_render_fused(const hrf_field* f, const hrf_samples* s /* ray-batch form */, const int32_t* ray_offsets /* [R+1] */,
+                     int64_t num_rays, float step, const float* background /* [R,3] or NULL */, const void* feat_in_bf16,
+                     const int32_t* feat_index, float* color /* [R,3] */, float* weights_sum /* [R] */, void* workspace,
+                     void* stream);
+
 /* Density-only pass of prune_samples (volume_rendering.py:66-84) with an exact early stop: ray chunks are
  * evaluated front to back; once a ray's accumulated optical depth makes every later sample fail nerfacc's
  * transmittance test (T < 1e-4) those samples are reported with sigma = 0 without being evaluated.  The kept

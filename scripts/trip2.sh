@@ -21,5 +21,7 @@ train featgrid HRF_TRAIN_REUSE=feat+grid
 train featgrid_ctas5 HRF_TRAIN_REUSE=feat+grid HRF_SCATTER_CTAS=5
 train featgrid_v1 HRF_TRAIN_REUSE=feat+grid HRF_SCATTER_V2=0
 tail -3 gpurun_out/train_*.err
+timeout 300 python bench.py --mode image --steps 3 --warmup 3 > gpurun_out/b_image2.json 2> gpurun_out/b_image2.err; cat gpurun_out/b_image2.json; tail -3 gpurun_out/b_image2.err
+timeout 200 python bench.py --mode render --steps 20 --warmup 5 --no-cpu-baseline --no-companions > gpurun_out/b_render2.json 2> gpurun_out/b_render2.err; cat gpurun_out/b_render2.json; tail -3 gpurun_out/b_render2.err
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"grid_scatter_v2" -s 8 -c 1 -o gpurun_out/prof_r2b_scatter -f \
     python bench.py --mode train --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_scatter2.log 2>&1

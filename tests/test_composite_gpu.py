@@ -138,3 +138,76 @@ def test_early_stop_density_pass_gives_the_same_kept_set(cuda):
             masks.append(keep.clone())
         assert torch.equal(masks[0], masks[1])
         print(f"ragged={ragged}: {int(skipped.sum())} of {full.numel()} densities skipped, kept {int(masks[0].sum())}")
+
+
+@pytest.mark.parametrize("with_bg", [False, True])
+def test_fused_render_kernel_equals_forward_plus_composite(cuda, with_bg):
+    """hrf_render_fused (compositing as the epilogue of the field kernel; rays cut by 128-sample tile borders chained by
+    the fix-up kernel) vs hrf_field_forward + hrf_composite_forward on the same samples: rays shorter than a tile, rays
+    spanning 2..5 tiles, empty rays, a tail tile; then with a live sample count below the capacity."""
+    import ctypes as C
+
+    from helpers import make_pair
+    from humanrf_b200.volume_rendering import render_fused
+
+    _, m, frames = make_pair((6,), table_std=2.0)
+    nr = 150
+    b = synthetic_rays(nr, 600, frames, seed=13, ragged=True)          # 0..600 samples per ray, every 7th ray empty
+    g = {k: v.to(cuda).contiguous() for k, v in b.items() if k in ("o", "d", "frames", "t", "ri")}
+    n = g["t"].shape[0]
+    counts = torch.bincount(b["ri"], minlength=nr)
+    assert (counts == 0).any() and (counts > 512).any() and (counts < 128).any()
+    bg = torch.rand(nr, 3, generator=torch.Generator().manual_seed(1)).to(cuda) if with_bg else None
+    nat = m.native()
+    off = ray_offsets(g["ri"], nr)
+    sigma, _, rgb, _ = nat.forward(nat.samples_rays(g["o"], g["d"], g["frames"], g["t"], g["ri"]), 1, False, False)
+    col = torch.empty(nr, 3, device=cuda)
+    ws = torch.empty(nr, device=cuda)
+    L.check(L.lib().hrf_composite_forward(sigma.data_ptr(), rgb.data_ptr(), g["t"].data_ptr(), off.data_ptr(), nr, 4e-4, L.ptr(bg),
+                                          col.data_ptr(), ws.data_ptr(), None, L.stream()))
+    fcol, fws = render_fused(m, g["o"], g["d"], g["frames"], g["t"], g["ri"], nr, bg)
+    torch.testing.assert_close(fcol, col, rtol=0, atol=2e-6)
+    torch.testing.assert_close(fws.view(-1), ws, rtol=0, atol=2e-6)
+    assert (fws.view(-1)[counts.to(cuda) == 0] == 0).all()
+    # live count on the device below the capacity: the trailing samples must not be seen
+    cut = int(off[100].item())
+    count = torch.tensor([cut], dtype=torch.int64, device=cuda)
+    off_cut = off.clone()
+    off_cut[101:] = cut
+    fcol2, fws2 = render_fused(m, g["o"], g["d"], g["frames"], g["t"], g["ri"], nr, bg, count_dev=count, ray_offsets_dev=off_cut)
+    torch.testing.assert_close(fcol2[:100], fcol[:100], rtol=0, atol=0)
+    assert (fws2.view(-1)[100:] == 0).all()
+
+
+def test_prune_then_render_reuses_the_features_of_the_density_pass(cuda):
+    """prune_samples stores the composed features of the candidates on the batch; render() of that unchanged batch runs
+    the MLPs on them (no second encode): bit-identical to a render() that encodes again, with and without gradients; an
+    edited batch silently falls back to encoding."""
+    from helpers import input_batch_of, make_pair
+    from humanrf_b200.volume_rendering import prune_samples, render
+
+    _, m, frames = make_pair((6, 6), table_std=2.0)
+    b = synthetic_rays(200, 300, frames, seed=17, ragged=True)
+    ib = input_batch_of(b, cuda)
+    prune_samples(ib, m, is_training=False)
+    assert getattr(ib, "_hrf_reuse", None) is not None
+    bg = torch.rand(200, 3, device=cuda)
+    with torch.no_grad():
+        a = render(ib, m, bg, is_training=False)
+    ib2 = input_batch_of(b, cuda)
+    ib2.sample_distances, ib2.ray_indices = ib.sample_distances.clone(), ib.ray_indices.clone()   # same survivors, no stash
+    with torch.no_grad():
+        c = render(ib2, m, bg, is_training=False)
+    torch.testing.assert_close(a.color, c.color, rtol=0, atol=0)
+    torch.testing.assert_close(a.weights_sum, c.weights_sum, rtol=0, atol=0)
+    # with gradients: same forward values, gradients equal up to the scatter's atomic ordering
+    grads = []
+    for batch in (ib, ib2):
+        for p in m.hot_parameters():
+            p.grad = None
+        out = render(batch, m, bg, is_training=True)
+        (out.color.square().sum() + out.weights_sum.sum()).backward()
+        grads.append([p.grad.clone() for p in m.hot_parameters()])
+        torch.testing.assert_close(out.color.detach(), a.color, rtol=0, atol=2e-6)
+    for x, y in zip(*grads):
+        assert (x - y).norm() <= 1e-4 * y.norm() + 1e-12
