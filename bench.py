@@ -1,19 +1,25 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the HumanRF per-ray hot path on B200 (see DESIGN.md "Measurement").
 
-A step = one pass of the hot path over one synthetic batch (SURVEY 8d / BASELINE.md section 2):
-4096 rays x 512 samples = 2,097,152 samples, segment_sizes=(50,) (log2T=18), 8 distinct frames of 15..64:
-    --mode render (default): fused field forward (4 hash grids x 16 levels -> compose -> sigma MLP -> colour MLP
-                             on tcgen05) + per-ray compositing  ->  4096 ray colours          [rays/s]
-    --mode train           : render forward + loss + fused backward + fused Adam               [rays/s]
-`value` is timed with CUDA events per step (inputs resident in HBM, L2 flushed between steps); `e2e`
-goes through the public API (humanrf_b200.volume_rendering.render) with pinned HOST buffers, H2D and D2H
-inside the timed region.  `--impl reference` times the CPU oracle port of the same path (the reference's
-tcnn/nerfacc path is CUDA-only and not installable here) on the box's host cores.
+BASELINE.json's metric is "train rays/sec & render Mpix/s at 1/2/4/8 B200".  A step = one pass of the hot path over one
+synthetic batch (SURVEY 8d / BASELINE.md section 2): 4096 rays x 512 samples = 2,097,152 candidate samples per GPU,
+segment_sizes=(50,) (log2T=18), 8 distinct frames of 15..64:
+    --mode train (default, configs[2]): jitter + prune pass (early-stop density over all candidates, keeps the composed
+                  features) + MLP-only forward of the survivors + compositing + loss + backward (tensor-core MLP backward,
+                  parity-slot table scatter) + gradient exchange (N > 1) + fused Adam                      [rays/s]
+    --mode render (configs[1]'s kernel): the fused inference kernel, encode -> MLPs -> compositing in one launch,
+                  over all 2,097,152 samples                                                               [rays/s]
+    --mode image (configs[1]/[4]): full 1028x752 images, sampler -> prune -> fused render, tile-sharded over ranks [Mpix/s]
+`value` is timed with CUDA events per step (inputs resident in HBM, L2 flushed between steps); `e2e` goes through the
+public API (FusedTrainer.step / volume_rendering.render) with pinned HOST buffers, H2D and D2H inside the timed region.
+The default (train) line at N=1 also carries `render` and `image` (each measured in its own process right after).
+`--impl reference` times the CPU oracle port of the same path (the reference's tcnn/nerfacc path is CUDA-only and not
+installable here) on the box's host cores.
 """
 from __future__ import annotations
 
 import argparse
+import csv
 import json
 import os
 import subprocess
@@ -27,24 +33,59 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 RAYS, SPR = 4096, 512
-SEGMENTS = (50,)
+SEGMENTS = tuple(int(x) for x in os.environ.get("HRF_BENCH_SEGMENTS", "50").split(","))
 ALG_BYTES_FWD = 3084          # 2048 B table gathers + 1024 B vector taps + 12 B stream, per sample
+ALG_BYTES_SCATTER = 6144      # SURVEY 8d backward convention: table-gradient RMW 2 x 2048 B + vector-gradient RMW 2 x 1024 B
 METRIC = {"render": "render_rays_per_s", "train": "train_rays_per_s", "image": "render_mpix_per_s"}
+UNIT = {"render": "rays/s", "train": "rays/s", "image": "Mpix/s"}
 
 
 def dist_info():
-    rank = int(os.environ.get("RANK", 0))
-    world = int(os.environ.get("WORLD_SIZE", 1))
-    local = int(os.environ.get("LOCAL_RANK", 0))
-    return rank, world, local
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 
 
 def load_peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
-        d = json.loads(p.read_text())
-        return float(d["hbm_gbs"]), "measured"
+        return float(json.loads(p.read_text())["hbm_gbs"]), "measured"
     return 6650.0, "fallback"
+
+
+def committed_ncu(kernel_substr):
+    """Per-launch figures of a kernel from the newest committed `ncu --set full` export under profiles/ that contains it
+    (a measurement, not a constant in this file): DRAM bytes, L1TEX / L2 throughput %, issue-slot %."""
+    unit_scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for f in sorted((ROOT / "profiles").glob("r2*_ncu_full_*_raw.csv"), key=lambda p: p.name, reverse=True):
+        try:
+            rows = list(csv.reader(open(f)))
+        except OSError:
+            continue
+        if len(rows) < 3:
+            continue
+        h, units = rows[0], rows[1]
+        for r in rows[2:]:
+            d = dict(zip(h, r))
+            if kernel_substr not in d.get("Kernel Name", ""):
+                continue
+            u = dict(zip(h, units))
+
+            def num(k, scale=False):
+                try:
+                    v = float(d[k].replace(",", ""))
+                except (KeyError, ValueError):
+                    return None
+                return v * unit_scale.get(u.get(k, ""), 1.0) if scale else v
+
+            rd, wr = num("dram__bytes_read.sum", True), num("dram__bytes_write.sum", True)
+            return {"traffic": None if rd is None or wr is None else rd + wr, "source": f"profiles/{f.name}",
+                    "kernel_name": d["Kernel Name"],
+                    "l1tex_pct": num("l1tex__throughput.avg.pct_of_peak_sustained_active"),
+                    "l2_pct": num("lts__throughput.avg.pct_of_peak_sustained_elapsed"),
+                    "dram_pct": num("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+                    "issue_slots_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                    "tensor_pipe_pct": num("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+                    "ncu_duration_ms": num("gpu__time_duration.sum")}
+    return None
 
 
 class ClockSampler:
@@ -94,11 +135,14 @@ def build_workload(device, seed):
     return model, frames, batch
 
 
-def cpu_oracle_rate(steps=3, warmup=1, rays_per_worker=16):
-    """Reference arm / cpu_baseline: the CPU oracle port of encode+MLP+composite on a bounded sample of the same
-    workload, one single-threaded worker per host core (oracle/cpu_bench.py, run in a fresh process)."""
+def cpu_oracle_rate(mode, steps=3, warmup=1, budget_s=20.0):
+    """Reference arm / cpu_baseline: the CPU oracle port of the same path on a bounded sample of the same workload, one
+    single-threaded worker per host core (oracle/cpu_bench.py, run in a fresh process).  The sample is sized from a
+    calibration step so that `steps + warmup` steps take about `budget_s` seconds (at least 16 rays per worker: with
+    fewer, process-pool overhead dominates and the figure moves 4x between boxes)."""
     cmd = [sys.executable, str(ROOT / "oracle" / "cpu_bench.py"), "--steps", str(steps), "--warmup", str(warmup),
-           "--rays-per-worker", str(rays_per_worker), "--samples-per-ray", str(SPR), "--segments", *map(str, SEGMENTS)]
+           "--budget-s", str(budget_s), "--samples-per-ray", str(SPR), "--mode", "train" if mode == "train" else "render",
+           "--segments", *map(str, SEGMENTS)]
     out = subprocess.run(cmd, capture_output=True, text=True, check=True).stdout.strip().splitlines()[-1]
     r = json.loads(out)
     return r["rays_per_s"], r["cores"], r["sample"], r
@@ -109,15 +153,15 @@ def companion_line(mode, steps):
     cmd = [sys.executable, str(ROOT / "bench.py"), "--mode", mode, "--steps", str(steps), "--warmup", "3", "--no-cpu-baseline",
            "--no-companions"]
     try:
-        r = subprocess.run(cmd, capture_output=True, text=True, timeout=150)
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=200)
         full = json.loads([ln for ln in r.stdout.strip().splitlines() if ln.startswith("{")][-1])
-        keep = {k: full.get(k) for k in ("metric", "value", "unit", "steps", "warmup", "ms_per_step", "gpu_launches")}
+        keep = {k: full.get(k) for k in ("metric", "value", "unit", "steps", "warmup", "ms_per_step", "gpu_launches", "clocks")}
         keep["e2e"] = (full.get("e2e") or {}).get("value")
         keep["workload"] = (full.get("config") or {}).get("workload")
         if full.get("roofline"):
-            keep["roofline_frac"], keep["roofline_kernel"] = full["roofline"].get("frac"), full["roofline"].get("kernel")
+            keep["roofline"] = {k: full["roofline"].get(k) for k in ("kernel", "frac", "achieved", "kernel_ms", "traffic")}
         return keep
-    except Exception as e:  # noqa: BLE001 -- the render line must still be printed
+    except Exception as e:  # noqa: BLE001 -- the headline line must still be printed
         return {"error": f"{type(e).__name__}: {e}"[:300]}
 
 
@@ -125,12 +169,14 @@ def run_reference(args):
     rank, world, _ = dist_info()
     if rank != 0:
         return
-    value, cores, sample, r = cpu_oracle_rate(steps=args.steps, warmup=args.warmup, rays_per_worker=4)
-    line = {"impl": "reference", "metric": METRIC[args.mode], "value": value, "unit": "rays/s", "n_gpus": args.gpus,
+    mode = "render" if args.mode == "image" else args.mode
+    value, cores, sample, r = cpu_oracle_rate(mode, steps=args.steps, warmup=args.warmup, budget_s=120.0)
+    line = {"impl": "reference", "metric": METRIC[mode], "value": value, "unit": "rays/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{RAYS} rays x {SPR} samples, segment_sizes={SEGMENTS}, render forward; each step = "
-                                   f"{r['rays_per_step']} rays of it", "note":
+            "config": {"workload": f"{RAYS} rays x {SPR} samples, segment_sizes={SEGMENTS}, "
+                                   f"{'prune + fwd + bwd + Adam' if mode == 'train' else 'render forward'}; each step = "
+                                   f"{r['rays_per_step']} rays of it", "mode": mode, "note":
                        "CPU oracle port of the reference path (tcnn/nerfacc are CUDA-only and not installable offline)"},
             "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -138,17 +184,16 @@ def run_reference(args):
 
 
 def run_image(args, dev, rank, world):
-    """BASELINE configs[1]/[4]: full 1028x752 images through sampler -> prune -> render, tile-sharded over the ranks
+    """BASELINE configs[1]/[4]: full 1028x752 images through sampler -> prune -> fused render, tile-sharded over the ranks
     (contiguous pixel ranges, no collective), image assembled on the device.  Mpix/s counts every pixel of the
     image, including background pixels the sampler masks out."""
     import numpy as np
     import torch.distributed as dist
 
-    from humanrf_b200.synthetic_scene import make_scene
-
     from humanrf_b200.dataset.occupancy_grid_native import OccupanyGrid
     from humanrf_b200.parallel import TileShardedRenderer
     from humanrf_b200.synthetic import make_model
+    from humanrf_b200.synthetic_scene import make_scene
 
     W, H, G = 1028, 752, 256
     model, frames = make_model(SEGMENTS, seed=123, device=dev)
@@ -159,31 +204,38 @@ def run_image(args, dev, rank, world):
                grid_handles=torch.tensor([og.add_grid(t(sc["grids"][0]))], dtype=torch.int64, device=dev),
                landscape=t(sc["landscape"]), inverse_krs=t(sc["inverse_krs"]), camera_origins=t(sc["camera_origins"]),
                aabb=t(sc["aabb"]), G=G, width=W, height=H)
-    r = TileShardedRenderer(model, og, rays_per_batch=65536)
+    r = TileShardedRenderer(model, og, rays_per_batch=262144)
+    clocks = ClockSampler(dist_info()[2])
     for _ in range(max(args.warmup, 3)):
         r.render_image_sharded(cam, rank, world)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    host = torch.empty(((W * H + world - 1) // world + 1, 3)).pin_memory()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         s, e, img = r.render_image_sharded(cam, rank, world)
-        host = img.cpu()                                   # D2H of this rank's tile (the step's result)
+        host[: e - s].copy_(img, non_blocking=True)        # D2H of this rank's tile (the step's result)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    clk = clocks.stop()
     if rank == 0:
         mpix = W * H * args.steps / float(dt.item()) / 1e6
-        frac = float((host.abs().sum(1) > 0).float().mean())
+        frac = float((host[: e - s].abs().sum(1) > 0).float().mean())
+        cand = r.last_stats.get("candidate_samples")
         print(json.dumps({"metric": METRIC["image"], "value": mpix, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
                           "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * float(dt.item()) / args.steps,
                           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
                           "data": "synthetic", "config": {"workload": f"{W}x{H} image, synthetic ellipsoid occupancy G={G}, "
-                                                         f"segment_sizes={SEGMENTS}, sampler+prune+render, 65536 rays/batch, "
-                                                         "wall clock incl. the per-batch host reads", "object_pixel_fraction_rank0": frac},
+                                                         f"segment_sizes={SEGMENTS}, sampler + prune pass + fused MLP/composite render, "
+                                                         "262144 rays/batch, wall clock incl. the sampler's host read per batch",
+                                                         "object_pixel_fraction_rank0": frac, "candidate_samples_rank0": cand,
+                                                         "l2": "working set (candidate arrays + features) far above the 126 MB L2"},
+                          "clocks": clk, "gpu_launches": None,
                           "e2e": {"value": mpix, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": W * H * 12 // world}}))
     if world > 1:
         dist.destroy_process_group()
@@ -195,10 +247,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default="render", choices=["render", "train", "image"])
+    ap.add_argument("--mode", default="train", choices=["train", "render", "image"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-companions", action="store_true",
-                    help="do not append the train / full-image numbers to the default render line")
+                    help="do not append the render / full-image numbers to the default train line")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -213,60 +265,48 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from humanrf_b200 import _lib as L
-    from humanrf_b200.volume_rendering import ray_offsets, render
+    from humanrf_b200.volume_rendering import ray_offsets, render, render_fused
 
     L.lib()
     if args.mode == "image":
         return run_image(args, dev, rank, world)
     model, frames, b = build_workload(dev, seed=123 + rank)
+    trainer = None
     if args.mode == "train":
         from humanrf_b200.dataset.input_batch import InputBatch as _IB
         from humanrf_b200.training import FusedTrainer
 
         # Stationary training workload: the ground truth is the initial model's own rendering ("teacher"), so the
         # model sits at a fixed point, the pruned sample count does not drift from step to step, and every step
-        # still does the full work (prune pass, forward, loss, backward, all-reduce, Adam with lr = 1e-2).
+        # still does the full work (prune pass, forward, loss, backward, gradient exchange, Adam with lr = 1e-2).
         with torch.no_grad():
             tb = {k: v.to(dev).contiguous() for k, v in b.items() if k in ("o", "d", "frames", "t", "ri")}
             out = render(_IB(ray_origins=tb["o"], ray_directions=tb["d"], frame_numbers=tb["frames"].view(-1, 1),
                              sample_distances=tb["t"].view(-1, 1), ray_indices=tb["ri"]), model, None, is_training=False)
             w = out.weights_sum.clamp(min=1e-6)
             b["rgba"] = torch.cat((out.color / w, out.weights_sum), dim=1).clamp(0, 1).cpu()
-        trainer = FusedTrainer(model, lr=1e-2, world_size=world, reuse=os.environ.get("HRF_TRAIN_REUSE", "feat"),
+        trainer = FusedTrainer(model, lr=1e-2, world_size=world, reuse=os.environ.get("HRF_TRAIN_REUSE", "feat+grid"),
                                exchange=os.environ.get("HRF_TRAIN_EXCHANGE", "p2p"))
-    nat = model.native()
+        trainer.profile = True
     g = {k: v.to(dev).contiguous() for k, v in b.items() if k in ("o", "d", "frames", "t", "ri", "rgba")}
     n = g["t"].shape[0]
     bg = torch.rand(RAYS, 3, device=dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    samples = nat.samples_rays(g["o"], g["d"], g["frames"], g["t"], g["ri"])
-    sigma = torch.empty(n, device=dev)
-    rgb = torch.empty(n, 3, device=dev)
-    color = torch.empty(RAYS, 3, device=dev)
-    wsum = torch.empty(RAYS, device=dev)
-    import ctypes as C
-
-    lib = L.lib()
+    off_all = ray_offsets(g["ri"], RAYS)
     launches = {"n": 0}
 
     def step_render(ev=None):
-        L.check(lib.hrf_field_forward(C.byref(nat.field), C.byref(samples), 1, 0, sigma.data_ptr(), None, rgb.data_ptr(),
-                                      None, None, L.stream()))
+        render_fused(model, g["o"], g["d"], g["frames"], g["t"], g["ri"], RAYS, bg, ray_offsets_dev=off_all)
         if ev is not None:
             ev.record()
-        off = ray_offsets(g["ri"], RAYS)
-        L.check(lib.hrf_composite_forward(sigma.data_ptr(), rgb.data_ptr(), g["t"].data_ptr(), off.data_ptr(), RAYS, 4e-4,
-                                          bg.data_ptr(), color.data_ptr(), wsum.data_ptr(), None, L.stream()))
-        launches["n"] += 3
+        launches["n"] += 2
 
-    kept, bwd_ev = [], []
+    kept, marks_all = [], []
 
     def step_train(ev=None):
-        be = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-        launches["n"] += trainer.step(g["o"], g["d"], g["frames"], g["t"], g["ri"], g["rgba"], RAYS, kernel_event=ev,
-                                      bwd_events=be)
+        launches["n"] += trainer.step(g["o"], g["d"], g["frames"], g["t"], g["ri"], g["rgba"], RAYS, kernel_event=ev)
         kept.append(trainer.last["samples"])
-        bwd_ev.append(be)
+        marks_all.append(trainer.last["marks"])
 
     step = step_render if args.mode == "render" else step_train
 
@@ -281,6 +321,7 @@ def main():
         step()
     barrier()
     launches["n"] = 0
+    kept.clear(), marks_all.clear()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     t_wall = time.perf_counter()
     for i in range(args.steps):
@@ -297,6 +338,17 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     total_ms = float(tt.item())
     gpu_launches = launches["n"]
+    phases = {}
+    if args.mode == "train":
+        for marks in marks_all:
+            for (_, e0), (name, e1) in zip(marks[:-1], marks[1:]):
+                phases[name] = phases.get(name, 0.0) + e0.elapsed_time(e1) / len(marks_all)
+        ph = torch.tensor([phases.get(k, 0.0) for k in sorted(phases)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ph, op=dist.ReduceOp.MAX)
+        phases = {k: float(v) for k, v in zip(sorted(phases), ph.tolist())}
+        trainer.profile = False
+        kept_mean = sum(int(k) for k in kept) / max(len(kept), 1)
 
     # ---- e2e through the public API with pinned host buffers -------------------------------------
     host = {k: b[k].contiguous().pin_memory() for k in ("o", "d", "frames", "t", "ri", "rgba")}
@@ -306,10 +358,11 @@ def main():
 
     from humanrf_b200.dataset.input_batch import InputBatch
 
-    # Render: three steps in flight on three streams (one pinned->device stream sustains ~16 GB/s on this host, scripts/e2e_probe.py), so step i+1's H2D copy and step i-1's D2H read overlap step i's
-    # kernels (copy engines beside the SMs) -- how a renderer walks the tiles of an image.  Train: steps are
-    # sequentially dependent (Adam), so only the next batch's H2D copy is prefetched on a copy stream.  Every step's
-    # copies are issued, and complete, inside the timed region.
+    # Render: three steps in flight on three streams (one pinned->device stream sustains ~16 GB/s on this host,
+    # scripts/e2e_probe.py), so step i+1's H2D copy and step i-1's D2H read overlap step i's kernels (copy engines beside
+    # the SMs) -- how a renderer walks the tiles of an image.  Train: steps are sequentially dependent (Adam), so the next
+    # batch's H2D copy is prefetched on a copy stream and the loss of step i is read back (pinned, asynchronously) while
+    # step i+1 runs.  Every step's copies are issued, and complete, inside the timed region.
     DEPTH = 3
     streams = [torch.cuda.Stream(dev) for _ in range(DEPTH)]
     host_colors = [host_color] + [torch.empty(RAYS, 3).pin_memory() for _ in range(DEPTH - 1)]
@@ -333,6 +386,8 @@ def main():
                 host_colors[i % DEPTH].copy_(out.color, non_blocking=True)
         torch.cuda.synchronize()
 
+    host_loss = torch.zeros(64).pin_memory()
+
     def e2e_train(k):
         nxt = upload(streams[0])
         for i in range(k):
@@ -340,15 +395,17 @@ def main():
             torch.cuda.current_stream().wait_event(done)
             if i + 1 < k:
                 nxt = upload(streams[0])
-            loss = trainer.step(bb["o"], bb["d"], bb["frames"], bb["t"], bb["ri"], bb["rgba"], RAYS, return_loss=True)
-            host_color[0, 0] = float(loss)  # the D2H read of the step's result (also fences bb before it is released)
+            trainer.step(bb["o"], bb["d"], bb["frames"], bb["t"], bb["ri"], bb["rgba"], RAYS)
+            host_loss[i % 64:i % 64 + 1].copy_(trainer.last["loss"].reshape(1), non_blocking=True)   # the D2H read of the step's result
+            for v in bb.values():
+                v.record_stream(torch.cuda.current_stream())
         torch.cuda.synchronize()
 
     e2e_loop = e2e_render if args.mode == "render" else e2e_train
-    e2e_loop(3)
+    e2e_loop(5)
     barrier()
     t0 = time.perf_counter()
-    k_e2e = max(6, args.steps // 2)
+    k_e2e = max(50, args.steps)
     e2e_loop(k_e2e)
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -366,49 +423,64 @@ def main():
         value = world * RAYS * args.steps / (total_ms * 1e-3)
         peak, which = load_peaks()
         if args.mode == "render":
-            alg_per_sample, roof_kernel = ALG_BYTES_FWD, "field_forward_kernel"
+            alg_per_sample, roof_kernel = ALG_BYTES_FWD, "field_forward_kernel<composite epilogue> (+ composite_fixup_kernel)"
             achieved = alg_per_sample * n / (kern_ms * 1e-3) / 1e9
+            prof = committed_ncu("field_forward_kernel")
+            note = ("SURVEY 8d convention: table gathers served by L2 count as algorithmic bytes; the physical limiter is the "
+                    "L1/TEX gather pipe, see l1tex_pct / issue_slots_pct")
         else:
-            # dominant kernels of the train step: field_backward_kernel + grid_scatter_kernel over the pruned samples.
-            # SURVEY 8d convention for the backward: table-gradient RMW 2 x 2048 B + vector-gradient RMW 2 x 1024 B +
-            # re-read of tables / vectors 3072 B = 9216 B per sample.
-            alg_per_sample, roof_kernel = 9216, "field_backward_kernel + grid_scatter_kernel"
-            kern_ms = sum(a.elapsed_time(b) for a, b in bwd_ev[-args.steps:]) / args.steps
-            kept = [int(k) for k in kept]
-            achieved = alg_per_sample * (sum(kept[-args.steps:]) / args.steps) / (kern_ms * 1e-3) / 1e9
+            # dominant kernel of the train step: the table-gradient scatter over the pruned samples
+            alg_per_sample, roof_kernel = ALG_BYTES_SCATTER, "grid_scatter_v2_kernel"
+            kern_ms = phases.get("scatter", 0.0)
+            achieved = alg_per_sample * kept_mean / max(kern_ms * 1e-3, 1e-9) / 1e9
+            prof = committed_ncu("grid_scatter")
+            note = ("SURVEY 8d backward convention: 2 x 2048 B table-gradient RMW + 2 x 1024 B vector-gradient RMW per surviving "
+                    "sample; the RMWs are L2 atomics (red.global.add.v2.f32), the physical limiter is issue slots / L2 RED rate")
         line = {
             "metric": METRIC[args.mode], "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"{RAYS} rays x {SPR} samples/ray = {n} samples per GPU, segment_sizes={SEGMENTS} (log2T=18), "
-                                   f"8 frames of 15..64, {'forward render' if args.mode == 'render' else 'fwd+bwd+Adam'}",
+            "config": {"workload": f"{RAYS} rays x {SPR} samples/ray = {n} samples per GPU, segment_sizes={SEGMENTS}, "
+                                   f"8 frames, {'fused forward render' if args.mode == 'render' else 'prune + fwd + bwd + exchange + Adam'}",
                        "mode": args.mode, "l2": "flushed between timed steps (256 MiB memset)", "parallelism": f"dp{world}",
-                       "samples_per_s": value * SPR,
-                       **({"samples_after_prune_mean": sum(kept[-args.steps:]) / args.steps,
-                           "note": "prune pass over all 2,097,152 candidates, fwd+bwd+Adam over the survivors; targets are the "
-                                   "initial model's own rendering so the workload is stationary"}
-                          if args.mode == "train" else {})},
-            "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                       "samples_per_s": value * SPR},
+            "e2e": {"value": e2e_val, "unit": "rays/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": k_e2e,
                     "api": "humanrf_b200.volume_rendering.render" if args.mode == "render" else "humanrf_b200.training.FusedTrainer.step",
-                    "pipelining": "3 steps in flight on 3 streams" if args.mode == "render" else "next batch's H2D prefetched on a copy stream"},
+                    "pipelining": "3 steps in flight on 3 streams" if args.mode == "render"
+                    else "next batch's H2D prefetched on a copy stream, loss read back asynchronously"},
             "gpu_launches": gpu_launches,
             "clocks": clk,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one field_forward_kernel launch on this very batch,
-                         # from the committed ncu --set full capture (profiles/r1_ncu_full_fwd_raw.csv)
-                         "traffic": 130.0e6 if args.mode == "render" else None, "traffic_unit": "bytes/launch",
-                         "peak_source": which, "kernel": roof_kernel, "kernel_ms": kern_ms, "algorithmic_bytes_per_sample": alg_per_sample},
+                         "traffic": prof["traffic"] if prof else None, "traffic_unit": "bytes/launch",
+                         "traffic_source": prof["source"] if prof else None,
+                         "peak_source": which, "kernel": roof_kernel, "kernel_ms": kern_ms,
+                         "algorithmic_bytes_per_sample": alg_per_sample, "note": note,
+                         **({k: prof[k] for k in ("l1tex_pct", "l2_pct", "dram_pct", "issue_slots_pct", "tensor_pipe_pct")} if prof else {})},
             "wall_s_timed_loop": t_wall,
         }
+        if args.mode == "train":
+            line["config"].update({"samples_after_prune_mean": kept_mean, "reuse": trainer.reuse, "exchange": trainer.exchange,
+                                   "note": "prune pass over all 2,097,152 candidates, fwd+bwd+Adam over the survivors; targets are the "
+                                           "initial model's own rendering so the workload is stationary"})
+            line["phases_ms"] = phases          # CUDA events inside FusedTrainer.step, mean over the timed steps, max over ranks
+            if world > 1:
+                line["allreduce_ms"] = phases.get("exchange+adam")
+                line["exchange"] = {"kind": trainer.exchange, "ms": phases.get("exchange+adam"),
+                                    "note": "barrier + fused reduce-scatter/Adam/shadow all-gather kernel over NVLink peer memory + "
+                                            "barrier + bucket memset; replaces the single-GPU Adam (see phases_ms at N=1)"}
         if world == 1 and not args.no_cpu_baseline:
-            v, cores, sample, _ = cpu_oracle_rate(steps=3, warmup=1, rays_per_worker=16)
+            v, cores, sample, _ = cpu_oracle_rate(args.mode, steps=2, warmup=1, budget_s=20.0)
             line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample}
-        if world == 1 and args.mode == "render" and not args.no_companions:
-            # BASELINE.json's metric is a pair ("train rays/sec & render Mpix/s"): the default line measures the fused
-            # render kernel chain on north_star's 4096 x 512 batch; the other two workloads run right after it (each in
-            # its own process, own timed region, same rules) and are attached here so one run reports all three.
-            line["companions"] = {m: companion_line(m, k) for m, k in (("train", args.steps), ("image", 3))}
+        if world == 1 and args.mode == "train" and not args.no_companions:
+            # BASELINE.json's metric is a pair ("train rays/sec & render Mpix/s"): the other two workloads run right after
+            # (each in its own process, own timed region, same rules) and are attached so one run reports all three.
+            line["render"] = companion_line("render", args.steps)
+            line["image"] = companion_line("image", 5)
+            line["config"]["render_rays_per_s"] = line["render"].get("value")
+            line["config"]["render_mpix_per_s"] = line["image"].get("value")
         print(json.dumps(line))
+    if trainer is not None:
+        trainer.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -1,5 +1,4 @@
-// Error plumbing, device info, fused Adam, bf16 cast, tcgen05 descriptor self-test and the
-// stand-alone tensor-composition op (tensor_composition.cu:9-118 parity).
+// Error plumbing, device info, fused Adam, bf16 cast and the tcgen05 descriptor self-test.
 #include <mutex>
 
 #include "field_common.cuh"
@@ -50,69 +49,6 @@ __global__ void adam_kernel(float* __restrict__ p, float* __restrict__ m, float*
 __global__ void cast_bf16_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ d, int64_t n) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) d[i] = __float2bfloat16_rn(s[i]);
-}
-
-// ---------------------------------------------------------------------------------------
-// tensor_composition_native parity (half features, fp32 vectors)
-// ---------------------------------------------------------------------------------------
-__global__ void compose_fwd_kernel(const __half* __restrict__ xyz, const __half* __restrict__ xyt,
-                                   const __half* __restrict__ yzt, const __half* __restrict__ xzt,
-                                   const float* __restrict__ vec, const float* __restrict__ coords, int64_t n, int F,
-                                   int VR, __half* __restrict__ out) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n * F) return;
-  const int fi = (int)(idx % F);
-  const int64_t si = idx / F;
-  float sv[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float c = coords[si * 4 + i] * VR - 0.5f;
-    const float fl = floorf(c);
-    const float fr = c - fl;
-    const int c0 = (int)fmaxf(fl, 0.f);
-    const int c1 = (int)fminf(fl + 1.f, (float)(VR - 1));
-    const float v0 = vec[((int64_t)i * VR + c0) * F + fi], v1 = vec[((int64_t)i * VR + c1) * F + fi];
-    sv[i] = v0 + fr * (v1 - v0);
-  }
-  const float r = __half2float(xyz[idx]) * sv[3] + __half2float(xyt[idx]) * sv[2] + __half2float(yzt[idx]) * sv[0] +
-                  __half2float(xzt[idx]) * sv[1];
-  out[idx] = __float2half(r);
-}
-
-// Backward: thread = (sample, feature); d_vectors via fp32 atomics exactly like the reference
-// (tensor_composition.cu:109-111).  The fused training path (field_bwd.cu) does not use this kernel.
-__global__ void compose_bwd_kernel(const __half* __restrict__ xyz, const __half* __restrict__ xyt,
-                                   const __half* __restrict__ yzt, const __half* __restrict__ xzt,
-                                   const float* __restrict__ vec, const float* __restrict__ coords,
-                                   const __half* __restrict__ dout, int64_t n, int F, int VR, __half* __restrict__ dxyz,
-                                   __half* __restrict__ dxyt, __half* __restrict__ dyzt, __half* __restrict__ dxzt,
-                                   float* __restrict__ dvec) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n * F) return;
-  const int fi = (int)(idx % F);
-  const int64_t si = idx / F;
-  const float feats[4] = {__half2float(yzt[idx]), __half2float(xzt[idx]), __half2float(xyt[idx]),
-                          __half2float(xyz[idx])};
-  const float d = __half2float(dout[idx]);
-  float sv[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float c = coords[si * 4 + i] * VR - 0.5f;
-    const float fl = floorf(c);
-    const float fr = c - fl;
-    const int c0 = (int)fmaxf(fl, 0.f);
-    const int c1 = (int)fminf(fl + 1.f, (float)(VR - 1));
-    const int64_t o0 = ((int64_t)i * VR + c0) * F + fi, o1 = ((int64_t)i * VR + c1) * F + fi;
-    const float v0 = vec[o0], v1 = vec[o1];
-    sv[i] = v0 + fr * (v1 - v0);
-    const float dv = feats[i] * d;
-    atomicAdd(dvec + o0, dv * (1.f - fr));
-    atomicAdd(dvec + o1, dv * fr);
-  }
-  dxyz[idx] = __float2half(sv[3] * d);
-  dxyt[idx] = __float2half(sv[2] * d);
-  dyzt[idx] = __float2half(sv[0] * d);
-  dxzt[idx] = __float2half(sv[1] * d);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -229,34 +165,6 @@ extern "C" int hrf_cast_bf16(const float* src, void* dst, int64_t n, void* strea
   if (n == 0) return 0;
   const int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)sm_count() * 8);
   cast_bf16_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, reinterpret_cast<__nv_bfloat16*>(dst), n);
-  HRF_CHECK_LAUNCH();
-  return 0;
-}
-
-extern "C" int hrf_compose_tensors_forward(const void* xyz, const void* xyt, const void* yzt, const void* xzt,
-                                           const float* vectors, const float* coords, int64_t n, int feature_dim,
-                                           int vec_res, void* out, void* stream) {
-  if (n == 0) return 0;
-  const int64_t total = n * feature_dim;
-  compose_fwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      (const __half*)xyz, (const __half*)xyt, (const __half*)yzt, (const __half*)xzt, vectors, coords, n, feature_dim,
-      vec_res, (__half*)out);
-  HRF_CHECK_LAUNCH();
-  return 0;
-}
-
-extern "C" int hrf_compose_tensors_backward(const void* xyz, const void* xyt, const void* yzt, const void* xzt,
-                                            const float* vectors, const float* coords, const void* d_out, int64_t n,
-                                            int feature_dim, int vec_res, void* d_xyz, void* d_xyt, void* d_yzt,
-                                            void* d_xzt, float* d_vectors, void* stream) {
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  HRF_CUDA(cudaMemsetAsync(d_vectors, 0, sizeof(float) * 4 * (size_t)vec_res * feature_dim, st));  // :188 zeros_like
-  if (n == 0) return 0;
-  const int64_t total = n * feature_dim;
-  compose_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-      (const __half*)xyz, (const __half*)xyt, (const __half*)yzt, (const __half*)xzt, vectors, coords,
-      (const __half*)d_out, n, feature_dim, vec_res, (__half*)d_xyz, (__half*)d_xyt, (__half*)d_yzt, (__half*)d_xzt,
-      d_vectors);
   HRF_CHECK_LAUNCH();
   return 0;
 }

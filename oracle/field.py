@@ -139,6 +139,7 @@ class OracleModel:
     density_scale: float = 100.0
     bf16: bool = False
     camera_embeddings: torch.Tensor = None   # [160, E] or None (humanrf.py:75-76)
+    sparse_grad: bool = False                # table gradients as sparse tensors (CPU training baseline only)
 
     def parameters(self):
         ps = []
@@ -164,10 +165,11 @@ class OracleModel:
                 continue
             c = xyzt[m]
             g = [self._q(t) for t in sd.grids]
-            e = [hashgrid.encode(g[0], c[:, [0, 1, 2]], sd.log2T),
-                 hashgrid.encode(g[1], c[:, [0, 1, 3]], sd.log2T),
-                 hashgrid.encode(g[2], c[:, [1, 2, 3]], sd.log2T),
-                 hashgrid.encode(g[3], c[:, [0, 2, 3]], sd.log2T)]
+            sp = self.sparse_grad
+            e = [hashgrid.encode(g[0], c[:, [0, 1, 2]], sd.log2T, sp),
+                 hashgrid.encode(g[1], c[:, [0, 1, 3]], sd.log2T, sp),
+                 hashgrid.encode(g[2], c[:, [1, 2, 3]], sd.log2T, sp),
+                 hashgrid.encode(g[3], c[:, [0, 2, 3]], sd.log2T, sp)]
             feats = feats.index_add(0, m, compose(e[0], e[1], e[2], e[3], sd.vectors, c))
         return self._q(feats)
 

@@ -82,9 +82,11 @@ def corner_indices_and_weights(x: np.ndarray, scale: np.float32, res: int, size:
     return idx, w
 
 
-def encode(table: torch.Tensor, x: torch.Tensor, log2_hashmap_size: int) -> torch.Tensor:
+def encode(table: torch.Tensor, x: torch.Tensor, log2_hashmap_size: int, sparse_grad: bool = False) -> torch.Tensor:
     """table: [entries, 2] float (any grad-enabled leaf); x: [N,3] float32 in [0,1].
-    Returns [N, 32] float32, level-major feature pairs; fp32 blend (fma accumulate order 0..7)."""
+    Returns [N, 32] float32, level-major feature pairs; fp32 blend (fma accumulate order 0..7).
+    sparse_grad: gather through an embedding lookup whose gradient is a sparse tensor (same values; the CPU training
+    baseline uses it so that 64 gathers per grid do not each allocate a dense zero gradient of the whole table)."""
     scales, ress, offs, sizes, hashed, total = level_table(log2_hashmap_size)
     assert table.shape[0] == total, (table.shape, total)
     xn = x.detach().cpu().numpy().astype(np.float32)
@@ -93,7 +95,10 @@ def encode(table: torch.Tensor, x: torch.Tensor, log2_hashmap_size: int) -> torc
         idx, w = corner_indices_and_weights(xn, scales[l], int(ress[l]), int(sizes[l]), bool(hashed[l]))
         idx_t = torch.from_numpy(idx + int(offs[l]))
         w_t = torch.from_numpy(w).to(table.dtype)
-        vals = table[idx_t.reshape(-1)].reshape(-1, 8, 2)
+        if sparse_grad:
+            vals = torch.nn.functional.embedding(idx_t.reshape(-1), table, sparse=True).reshape(-1, 8, 2)
+        else:
+            vals = table[idx_t.reshape(-1)].reshape(-1, 8, 2)
         acc = torch.zeros((xn.shape[0], 2), dtype=table.dtype)
         for c in range(8):
             acc = acc + w_t[:, c:c + 1] * vals[:, c]

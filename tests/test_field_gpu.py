@@ -116,3 +116,40 @@ def test_camera_embeddings(cuda, training):
     _check(out.density.cpu().numpy(), out.radiance.cpu().numpy(), osig.numpy(), orgb.numpy(), f"cam-emb training={training}")
     assert np.abs(orgb.numpy() - orgb_other.numpy()).max() > 2e-2, "the embedding must matter for this check to mean anything"
     assert len(m.get_params(1e-2)) == 4 and "camera_embeddings.weight" in m.state_dict()
+
+
+@pytest.mark.parametrize("F,ordered", [(32, True), (32, False), (5, False), (2, True)])
+def test_stand_alone_tensor_composition_matches_oracle(cuda, F, ordered):
+    """hrf_compose_tensors_forward/backward (csrc/compose.cu: feature-pair threads walking consecutive samples, run-length
+    vector-gradient accumulation) vs the oracle's restatement of tensor_composition.cu:30-54,85-117 in float64.
+    ordered = coordinates that move slowly from sample to sample (rays: long tap runs) vs random (a run per sample)."""
+    from humanrf_b200.scene_representation import tensor_composition_native as ours
+    from oracle import field as OF
+
+    g = torch.Generator().manual_seed(F * 2 + ordered)
+    n, VR = 3001, 64
+    feats = [torch.randn(n, F, generator=g).half() for _ in range(4)]
+    vec = torch.randn(4, VR, F, generator=g) * 0.3
+    if ordered:
+        coords = (torch.rand(1, 4, generator=g) + torch.arange(n).view(-1, 1) * torch.tensor([[3e-4, -2e-4, 1e-4, 0.0]])).remainder(1.0)
+    else:
+        coords = torch.rand(n, 4, generator=g)
+    coords[:7] = 0.0
+    coords[7:14] = 1.0
+    dout = torch.randn(n, F, generator=g).half()
+    f64 = [f.double().requires_grad_(True) for f in feats]
+    v64 = vec.double().requires_grad_(True)
+    ref = OF.compose(*f64, v64, coords)                                         # fp32 tap arithmetic, float64 blend
+    (ref * dout.double()).sum().backward()
+    dev = [f.to(cuda) for f in feats]
+    out = ours.compose_tensors_forward(*dev, vec.to(cuda), coords.to(cuda))
+    assert out.dtype == torch.float16 and out.shape == (n, F)
+    err = (out.double().cpu() - ref.detach()).abs()
+    assert (err <= 2.0 ** -10 * ref.detach().abs() + 1e-4).all(), err.max()
+    res = ours.compose_tensors_backward(*dev, vec.to(cuda), coords.to(cuda), dout.to(cuda))
+    for got, want in zip(res[:4], f64):
+        e = (got.double().cpu() - want.grad).abs()
+        assert (e <= 2.0 ** -10 * want.grad.abs() + 1e-4).all(), e.max()
+    dv = res[4].double().cpu()
+    assert ((dv != 0) & (v64.grad == 0)).sum() == 0
+    assert (dv - v64.grad).norm() <= 1e-5 * v64.grad.norm()
