@@ -9,7 +9,9 @@ segment_sizes=(50,) (log2T=18), 8 distinct frames of 15..64:
                   parity-slot table scatter) + gradient exchange (N > 1) + fused Adam                      [rays/s]
     --mode render (configs[1]'s kernel): the fused inference kernel, encode -> MLPs -> compositing in one launch,
                   over all 2,097,152 samples                                                               [rays/s]
-    --mode image (configs[1]/[4]): full 1028x752 images, sampler -> prune -> fused render, tile-sharded over ranks [Mpix/s]
+    --mode image (configs[1]): full 1028x752 images, sampler -> prune -> fused render, tile-sharded over ranks       [Mpix/s]
+    --mode sweep (configs[4]): the novel-view sweep, whole images of a (camera, frame) sequence dealt round-robin to the
+                  ranks (actorshq/evaluation/presets.py:58-86), `--steps` images per rank, no collective          [Mpix/s]
 `value` is timed with CUDA events per step (inputs resident in HBM, L2 flushed between steps); `e2e` goes through the
 public API (FusedTrainer.step / volume_rendering.render) with pinned HOST buffers, H2D and D2H inside the timed region.
 The default (train) line at N=1 also carries `render` and `image` (each measured in its own process right after).
@@ -36,8 +38,8 @@ RAYS, SPR = 4096, 512
 SEGMENTS = tuple(int(x) for x in os.environ.get("HRF_BENCH_SEGMENTS", "50").split(","))
 ALG_BYTES_FWD = 3084          # 2048 B table gathers + 1024 B vector taps + 12 B stream, per sample
 ALG_BYTES_SCATTER = 6144      # SURVEY 8d backward convention: table-gradient RMW 2 x 2048 B + vector-gradient RMW 2 x 1024 B
-METRIC = {"render": "render_rays_per_s", "train": "train_rays_per_s", "image": "render_mpix_per_s"}
-UNIT = {"render": "rays/s", "train": "rays/s", "image": "Mpix/s"}
+METRIC = {"render": "render_rays_per_s", "train": "train_rays_per_s", "image": "render_mpix_per_s", "sweep": "render_mpix_per_s"}
+UNIT = {"render": "rays/s", "train": "rays/s", "image": "Mpix/s", "sweep": "Mpix/s"}
 
 
 def dist_info():
@@ -169,7 +171,7 @@ def run_reference(args):
     rank, world, _ = dist_info()
     if rank != 0:
         return
-    mode = "render" if args.mode == "image" else args.mode
+    mode = "render" if args.mode in ("image", "sweep") else args.mode
     value, cores, sample, r = cpu_oracle_rate(mode, steps=args.steps, warmup=args.warmup, budget_s=120.0)
     line = {"impl": "reference", "metric": METRIC[mode], "value": value, "unit": "rays/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds_per_step"], "higher_is_better": True,
@@ -206,6 +208,8 @@ def run_image(args, dev, rank, world):
                aabb=t(sc["aabb"]), G=G, width=W, height=H)
     r = TileShardedRenderer(model, og, rays_per_batch=262144)
     clocks = ClockSampler(dist_info()[2])
+    if args.mode == "sweep":
+        return run_sweep(args, dev, rank, world, model, frames, r, clocks, W, H, G)
     for _ in range(max(args.warmup, 3)):
         r.render_image_sharded(cam, rank, world)
     if world > 1:
@@ -241,13 +245,69 @@ def run_image(args, dev, rank, world):
         dist.destroy_process_group()
 
 
+def run_sweep(args, dev, rank, world, model, frames, renderer, clocks, W, H, G):
+    """BASELINE configs[4]: 160 cameras x 50 frames = 8000 whole images, dealt round-robin to the ranks.  A bench run renders
+    `--steps` images PER RANK of that sequence (synthetic ring of 160 cameras, 2 distinct occupancy grids, frames 15..64)."""
+    import numpy as np
+    import torch.distributed as dist
+
+    from humanrf_b200.parallel import deal_round_robin
+    from humanrf_b200.synthetic_scene import make_scene
+
+    n_cams, n_frames = 160, min(50, len(frames))
+    sc = make_scene(num_images=n_cams, width=W, height=H, G=G, portrait_every=0)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    handles = [renderer.og.add_grid(t(sc["grids"][0]))]
+    ikr, org, aabb = t(sc["inverse_krs"]), t(sc["camera_origins"]), t(sc["aabb"])
+    sequence = [(c, frames[f]) for f in range(n_frames) for c in range(n_cams)]          # presets.py:58-86 order: frame-major
+    mine = deal_round_robin(sequence[: (max(args.warmup, 3) + args.steps) * world], rank, world)
+
+    def cam_of(c, f):
+        return dict(frame_numbers=torch.tensor([f], dtype=torch.int32, device=dev),
+                    camera_numbers=torch.tensor([c], dtype=torch.int32, device=dev),
+                    grid_handles=torch.tensor(handles, dtype=torch.int64, device=dev), landscape=torch.tensor([True], device=dev),
+                    inverse_krs=ikr[c:c + 1].contiguous(), camera_origins=org[c:c + 1].contiguous(), aabb=aabb, G=G, width=W, height=H)
+
+    w = max(args.warmup, 3)
+    for c, f in mine[:w]:
+        renderer.render_range(cam_of(c, f), 0, W * H)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    host = torch.empty((W * H, 3)).pin_memory()
+    t0 = time.perf_counter()
+    for c, f in mine[w:]:
+        img = renderer.render_range(cam_of(c, f), 0, W * H)
+        host.copy_(img, non_blocking=True)                 # each finished image leaves the device
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    clk = clocks.stop()
+    if rank == 0:
+        images = args.steps * world
+        mpix = W * H * images / float(dt.item()) / 1e6
+        print(json.dumps({"metric": METRIC["sweep"], "value": mpix, "unit": "Mpix/s", "n_gpus": world, "steps": args.steps,
+                          "warmup": w, "ms_per_step": 1e3 * float(dt.item()) / args.steps, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                          "config": {"workload": f"novel-view sweep: {images} of 160 cameras x {n_frames} frames = {n_cams * n_frames} images "
+                                                 f"({W}x{H}), round-robin over {world} rank(s), segment_sizes={SEGMENTS}",
+                                     "images_per_rank": args.steps, "full_sweep_estimate_s": n_cams * n_frames / images * float(dt.item())},
+                          "clocks": clk, "gpu_launches": None,
+                          "e2e": {"value": mpix, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": W * H * 12}}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default="train", choices=["train", "render", "image"])
+    ap.add_argument("--mode", default="train", choices=["train", "render", "image", "sweep"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-companions", action="store_true",
                     help="do not append the render / full-image numbers to the default train line")
@@ -268,7 +328,7 @@ def main():
     from humanrf_b200.volume_rendering import ray_offsets, render, render_fused
 
     L.lib()
-    if args.mode == "image":
+    if args.mode in ("image", "sweep"):
         return run_image(args, dev, rank, world)
     model, frames, b = build_workload(dev, seed=123 + rank)
     trainer = None

@@ -50,6 +50,52 @@ __device__ __forceinline__ void red2(float* addr, float a, float b) {
   //  the next step behind the REDs of this one)
   asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b));
 }
+// Table entries of the 8 vertices of a cell in parity-slot order (slot bit a = parity of the vertex coordinate on axis a).
+// hashed: tcnn's coherent prime hash; dense: x + y res + z res^2, one conditional subtraction (cell inside the grid).
+__device__ __forceinline__ void slot_indices(Cell A, Cell B, Cell C, bool hashed, uint32_t mulY, uint32_t mulZ, uint32_t hmask,
+                                             uint32_t lsize, uint32_t (&v)[8]) {
+  const uint32_t nx0 = (A.g + 1u) & ~1u, nx1 = A.g | 1u;                   // even / odd vertex on each axis
+  const uint32_t ny0 = ((B.g + 1u) & ~1u) * mulY, ny1 = (B.g | 1u) * mulY;
+  const uint32_t nz0 = ((C.g + 1u) & ~1u) * mulZ, nz1 = (C.g | 1u) * mulZ;
+  if (hashed) {   // (uniform over the warp unless the 32 x 8 samples straddle temporal segments of different sizes)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v[q] = (((q & 1) ? nx1 : nx0) ^ ((q & 2) ? ny1 : ny0) ^ ((q & 4) ? nz1 : nz0)) & hmask;
+  } else {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const uint32_t t = ((q & 1) ? nx1 : nx0) + ((q & 2) ? ny1 : ny0) + ((q & 4) ? nz1 : nz0);   // < 2 * lsize (see corner_indices)
+      v[q] = t >= lsize ? t - lsize : t;
+    }
+  }
+}
+
+// A sample whose cell lies outside a DENSE level's grid (a position outside the unit cube: only reachable through the
+// QueryInput API, never through ray batches inside the AABB): the forward wraps its indices with the general modulo
+// (corner_indices); the straight-line step below assumes one conditional subtraction.  Such samples take this cold,
+// out-of-line path: 8 direct REDs with exactly the forward's indices, and the two vector-row REDs.
+template <bool kGather>
+__device__ __noinline__ void scatter_sample_slow(const uint32_t* tab, float* gtab, float* gvec, const float* vecs, bool hashed,
+                                                 uint32_t res, uint32_t lsize, Cell A, Cell B, Cell C, VecTap tp, int l, float2 dO,
+                                                 uint32_t ev) {
+  uint32_t idx[8];
+  float w[8];
+  corner_indices(hashed, res, lsize, A, B, C, idx);
+  corner_weights(A, B, C, w);
+  const float2 v0 = __ldg(reinterpret_cast<const float2*>(vecs + tp.o0 + 2 * l)), v1 = __ldg(reinterpret_cast<const float2*>(vecs + tp.o1 + 2 * l));
+  const float gx = (v0.x + tp.frac * (v1.x - v0.x)) * dO.x, gy = (v0.y + tp.frac * (v1.y - v0.y)) * dO.y;
+  float ex = bf16_lo(ev), ey = bf16_hi(ev);
+  if (kGather) {
+    ex = ey = 0.f;
+    for (int q = 0; q < 8; ++q) {
+      const uint32_t r = __ldg(tab + idx[q]);
+      ex = __fmaf_rn(w[q], bf16_lo(r), ex), ey = __fmaf_rn(w[q], bf16_hi(r), ey);
+    }
+  }
+  for (int q = 0; q < 8; ++q) red2(gtab + 2 * (size_t)idx[q], w[q] * gx, w[q] * gy);
+  const float dx = ex * dO.x, dy = ey * dO.y;
+  red2(gvec + tp.o0 + 2 * l, dx * (1.f - tp.frac), dy * (1.f - tp.frac));
+  red2(gvec + tp.o1 + 2 * l, dx * tp.frac, dy * tp.frac);
+}
 
 // kGrid: 0 xyz, 1 xyt, 2 yzt, 3 xzt (decomposition4d.py:126-129); its vector axis is t, z, x, y (tensor_composition.cu:49-52)
 template <int kGrid, bool kGather>
@@ -82,7 +128,7 @@ __device__ __forceinline__ void scatter_levels(const ScatterV2Args& a, V2Smem& s
     const uint32_t res = f.level_res[l];
 
     uint32_t cur_sgi = 255u;
-    uint32_t idx[8], raw[8];      // table entry of the vertex each parity slot holds (0xffffffff: none yet), its bf16x2 value
+    uint32_t idx[8], raw[8];      // table entry of the vertex each parity slot holds, its bf16x2 value
     float accx[8], accy[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) accx[q] = accy[q] = 0.f, idx[q] = 0xffffffffu, raw[q] = 0u;
@@ -90,10 +136,9 @@ __device__ __forceinline__ void scatter_levels(const ScatterV2Args& a, V2Smem& s
     float* gvec = nullptr;
     const uint32_t* tab = nullptr;
     const float* vecs = nullptr;
-    uint32_t lsize = 1u, mulY = 0u, mulZ = 0u;
+    uint32_t lsize = 1u, mulY = 0u, mulZ = 0u, hmask = 0u;
     bool hashed = false;
-    uint32_t to0 = 0xffffffffu, to1 = 0u;
-    float2 tv0 = make_float2(0.f, 0.f), tv1 = make_float2(0.f, 0.f);
+    uint32_t to0 = 0u, to1 = 0u;          // current tap rows (valid once gtab != nullptr)
     float va0 = 0.f, va1 = 0.f, vb0 = 0.f, vb1 = 0.f;
 
 #pragma unroll 1
@@ -106,6 +151,8 @@ __device__ __forceinline__ void scatter_levels(const ScatterV2Args& a, V2Smem& s
       const float c1 = (kGrid == 0 || kGrid == 1) ? p4.y : p4.z;
       const float c2 = (kGrid == 0) ? p4.z : p4.w;
       const float cv = (kAxis == 0) ? p4.x : (kAxis == 1) ? p4.y : (kAxis == 2) ? p4.z : p4.w;
+      const VecTap tp = make_tap(cv, f.vec_res, kAxis);
+      const Cell A = to_cell(scale, c0), B = to_cell(scale, c1), C = to_cell(scale, c2);
       if (sgi != cur_sgi) {                             // (rare) new temporal segment: flush everything, new constants
         if (gtab != nullptr) {
 #pragma unroll
@@ -113,10 +160,8 @@ __device__ __forceinline__ void scatter_levels(const ScatterV2Args& a, V2Smem& s
             red2(gtab + 2 * (size_t)idx[q], accx[q], accy[q]);
             accx[q] = accy[q] = 0.f;
           }
-          if (to0 != 0xffffffffu) {
-            red2(gvec + to0 + 2 * l, va0, va1);
-            red2(gvec + to1 + 2 * l, vb0, vb1);
-          }
+          red2(gvec + to0 + 2 * l, va0, va1);
+          red2(gvec + to1 + 2 * l, vb0, vb1);
           va0 = va1 = vb0 = vb1 = 0.f;
         }
         const hrf_segment* sg = f.segments + sgi;
@@ -125,54 +170,50 @@ __device__ __forceinline__ void scatter_levels(const ScatterV2Args& a, V2Smem& s
         hashed = ((sg->hashed_mask >> l) & 1u) != 0u;
         mulY = hashed ? kPrimeY : res;
         mulZ = hashed ? kPrimeZ : res * res;
+        hmask = hashed ? lsize - 1u : 0xffffffffu;
         tab = sg->grid[kGrid] + off;
         vecs = sg->vectors;
         gvec = a.seg_grads[sgi].vectors;
         gtab = a.seg_grads[sgi].grid[kGrid] + 2 * (size_t)off;
-        to0 = 0xffffffffu;
+        // start the runs AT this sample: its own vertices / taps are the current ones, so the step below finds nothing to
+        // flush (the accumulators are zero) and the hot path needs no "slot is empty" test
+        to0 = tp.o0, to1 = tp.o1;
+        if (hashed || (A.g < res && B.g < res && C.g < res)) {
+          slot_indices(A, B, C, hashed, mulY, mulZ, hmask, lsize, idx);
+        } else {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) idx[q] = 0xffffffffu;
+          for (int q = 0; q < 8; ++q) idx[q] = 0u;       // (out-of-grid sample: any valid entry; it only ever receives +0)
+        }
+        if (kGather) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) raw[q] = __ldg(tab + idx[q]);
+        }
         cur_sgi = sgi;
       }
-      // ---- vector tap of this sample (tensor_composition.cu:37-45); a new tap pair flushes the gradient run
-      const VecTap tp = make_tap(cv, f.vec_res, kAxis);
-      const bool new_tap = tp.o0 != to0 || tp.o1 != to1;
-      if (new_tap) {
-        if (to0 != 0xffffffffu) {
-          red2(gvec + to0 + 2 * l, va0, va1);
-          red2(gvec + to1 + 2 * l, vb0, vb1);
-        }
+      uint32_t ev = 0u;
+      if (!kGather) ev = sm.eg[row + j];
+      if (!hashed && (A.g >= res || B.g >= res || C.g >= res)) {   // outside a dense grid (never for samples inside the AABB)
+        scatter_sample_slow<kGather>(tab, gtab, gvec, vecs, hashed, res, lsize, A, B, C, tp, l, dO, ev);
+        continue;
+      }
+      // ---- vector tap of this sample (tensor_composition.cu:37-45); a new tap pair flushes the gradient run.  The two
+      // rows are fetched every step (L1 hits, issued here, consumed after the index work below): no stall on them.
+      if (tp.o0 != to0 || tp.o1 != to1) {
+        red2(gvec + to0 + 2 * l, va0, va1);
+        red2(gvec + to1 + 2 * l, vb0, vb1);
         va0 = va1 = vb0 = vb1 = 0.f;
         to0 = tp.o0, to1 = tp.o1;
-        tv0 = __ldg(reinterpret_cast<const float2*>(vecs + to0 + 2 * l));
-        tv1 = __ldg(reinterpret_cast<const float2*>(vecs + to1 + 2 * l));
       }
+      const float2 tv0 = __ldg(reinterpret_cast<const float2*>(vecs + tp.o0 + 2 * l));
+      const float2 tv1 = __ldg(reinterpret_cast<const float2*>(vecs + tp.o1 + 2 * l));
       // ---- cell -> the 8 vertex indices in parity-slot order; a slot whose index changed is flushed and re-keyed
       // (two different vertices that hash to the same entry keep accumulating into one slot: same table entry anyway)
-      const Cell A = to_cell(scale, c0), B = to_cell(scale, c1), C = to_cell(scale, c2);
-      const uint32_t nx0 = (A.g + 1u) & ~1u, nx1 = A.g | 1u;                   // even / odd vertex on each axis
-      const uint32_t ny0 = ((B.g + 1u) & ~1u) * mulY, ny1 = (B.g | 1u) * mulY;
-      const uint32_t nz0 = ((C.g + 1u) & ~1u) * mulZ, nz1 = (C.g | 1u) * mulZ;
       uint32_t nidx[8];
-      if (hashed) {
-        const uint32_t m = lsize - 1u;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) nidx[q] = (((q & 1) ? nx1 : nx0) ^ ((q & 2) ? ny1 : ny0) ^ ((q & 4) ? nz1 : nz0)) & m;
-      } else {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          uint32_t v = ((q & 1) ? nx1 : nx0) + ((q & 2) ? ny1 : ny0) + ((q & 4) ? nz1 : nz0);
-          if (v >= lsize) {
-            v -= lsize;
-            if (v >= lsize) v = slow_mod(v, lsize);
-          }
-          nidx[q] = v;
-        }
-      }
+      slot_indices(A, B, C, hashed, mulY, mulZ, hmask, lsize, nidx);
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         if (nidx[q] != idx[q]) {
-          if (accx[q] != 0.f || accy[q] != 0.f) red2(gtab + 2 * (size_t)idx[q], accx[q], accy[q]);
+          red2(gtab + 2 * (size_t)idx[q], accx[q], accy[q]);
           accx[q] = accy[q] = 0.f;
           idx[q] = nidx[q];
           if (kGather) raw[q] = __ldg(tab + nidx[q]);
@@ -194,7 +235,6 @@ __device__ __forceinline__ void scatter_levels(const ScatterV2Args& a, V2Smem& s
       }
       float ex = 0.f, ey = 0.f;
       if (!kGather) {
-        const uint32_t ev = sm.eg[row + j];
         ex = bf16_lo(ev), ey = bf16_hi(ev);
       } else {
 #pragma unroll
@@ -210,12 +250,9 @@ __device__ __forceinline__ void scatter_levels(const ScatterV2Args& a, V2Smem& s
     }
     if (gtab != nullptr) {
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
-        if (accx[q] != 0.f || accy[q] != 0.f) red2(gtab + 2 * (size_t)idx[q], accx[q], accy[q]);
-      if (to0 != 0xffffffffu) {
-        if (va0 != 0.f || va1 != 0.f) red2(gvec + to0 + 2 * l, va0, va1);
-        if (vb0 != 0.f || vb1 != 0.f) red2(gvec + to1 + 2 * l, vb0, vb1);
-      }
+      for (int q = 0; q < 8; ++q) red2(gtab + 2 * (size_t)idx[q], accx[q], accy[q]);
+      red2(gvec + to0 + 2 * l, va0, va1);
+      red2(gvec + to1 + 2 * l, vb0, vb1);
     }
   }
 }

@@ -87,13 +87,28 @@ def prune_samples(input_batch: InputBatch, scene_representation: HumanRF, is_tra
     ib.sample_distances = out_t[:kept].view(-1, 1)
     ib.ray_indices = out_ri[:kept]
     # what a render() of this very batch can reuse: composed features of the candidates, the survivors' rows in them, the
-    # survivors' ray-offset table.  Tied to the identity of the two tensors above: any edit of the batch drops it.
-    ib._hrf_reuse = (saved, src[:kept], kept_off, ib.sample_distances, ib.ray_indices, id(scene_representation))
+    # survivors' ray-offset table.  Kept beside the batch (the reference's merge_input_batches walks vars(batch) and
+    # rejects anything that is not a tensor, input.py:17-22) and tied to the identity of the two tensors above: any edit
+    # of the batch drops it.
+    _remember(ib, (saved, src[:kept], kept_off, ib.sample_distances, ib.ray_indices, id(scene_representation)))
+
+
+_REUSE = {}      # id(batch) -> (weakref to the batch, payload); entries die with their batch
+
+
+def _remember(ib: InputBatch, payload) -> None:
+    import weakref
+
+    key = id(ib)
+    _REUSE[key] = (weakref.ref(ib, lambda _r, k=key: _REUSE.pop(k, None)), payload)
 
 
 def _reusable_features(ib: InputBatch, model: HumanRF):
-    r = getattr(ib, "_hrf_reuse", None)
-    if r is None or r[3] is not ib.sample_distances or r[4] is not ib.ray_indices or r[5] != id(model):
+    e = _REUSE.get(id(ib))
+    if e is None or e[0]() is not ib:
+        return None
+    r = e[1]
+    if r[3] is not ib.sample_distances or r[4] is not ib.ray_indices or r[5] != id(model):
         return None
     return r[0], r[1], r[2]
 

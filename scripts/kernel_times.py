@@ -31,12 +31,13 @@ def main():
     R, n0 = 4096, g["t"].shape[0]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def timeit(name, fn, reps=a.reps, note=""):
+    def timeit(name, fn, reps=a.reps, note="", cold=True):
         for _ in range(3):
             fn()
         ts = []
         for _ in range(reps):
-            flush.zero_()
+            if cold:
+                flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             fn()
@@ -53,6 +54,9 @@ def main():
     timeit("forward density-only (all candidates)", lambda: nat.forward(s_all, 0, False, False))
     timeit("forward render + save feat/egrid (all)", lambda: nat.forward(s_all, 1, False, True))
     timeit("prune pass: early-stop density", lambda: nat.density_early_stop(s_all, off0, R, 4e-4))
+    timeit("prune pass + save composed features", lambda: nat.density_early_stop(s_all, off0, R, 4e-4, save="feat"))
+    timeit("prune pass + save feat + per-grid feats", lambda: nat.density_early_stop(s_all, off0, R, 4e-4, save="feat+grid"))
+    timeit("prune pass (L2 warm)", lambda: nat.density_early_stop(s_all, off0, R, 4e-4), cold=False)
     # survivors
     sigma0 = nat.density_early_stop(s_all, off0, R, 4e-4)
     keep = torch.empty(n0, dtype=torch.uint8, device=dev)
@@ -95,8 +99,11 @@ def main():
     def scatter(eg):
         L.check(lib.hrf_field_backward_tables(C.byref(nat.field), C.byref(s), sg_dev.data_ptr(), eg, None, 0, ws.data_ptr(), 0, 4, L.stream()))
 
+    timeit("MLP-only forward from features (survivors)", lambda: nat.forward_from_features(s, feat, None))
     timeit("table scatter, saved egrid", lambda: scatter(egrid))
     timeit("table scatter, re-gather tables", lambda: scatter(None))
+    timeit("table scatter, saved egrid (L2 warm)", lambda: scatter(egrid), cold=False)
+    timeit("backward MLP kernel (L2 warm)", bwd_mlp, cold=False)
     tot = sum(p.numel() for p in model.hot_parameters())
     pm, pv = [torch.zeros_like(p) for p in model.hot_parameters()], [torch.zeros_like(p) for p in model.hot_parameters()]
 
