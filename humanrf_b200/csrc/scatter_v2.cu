@@ -140,6 +140,7 @@ __device__ __forceinline__ void scatter_levels(const ScatterV2Args& a, V2Smem& s
     bool hashed = false;
     uint32_t to0 = 0u, to1 = 0u;          // current tap rows (valid once gtab != nullptr)
     float va0 = 0.f, va1 = 0.f, vb0 = 0.f, vb1 = 0.f;
+    uint32_t slow_mask = 0u;
 
 #pragma unroll 1
     for (int j = 0; j < cnt; ++j) {
@@ -160,8 +161,8 @@ __device__ __forceinline__ void scatter_levels(const ScatterV2Args& a, V2Smem& s
             red2(gtab + 2 * (size_t)idx[q], accx[q], accy[q]);
             accx[q] = accy[q] = 0.f;
           }
-          red2(gvec + to0 + 2 * l, va0, va1);
-          red2(gvec + to1 + 2 * l, vb0, vb1);
+          red2(gvec + to0, va0, va1);
+          red2(gvec + to1, vb0, vb1);
           va0 = va1 = vb0 = vb1 = 0.f;
         }
         const hrf_segment* sg = f.segments + sgi;
@@ -172,8 +173,8 @@ __device__ __forceinline__ void scatter_levels(const ScatterV2Args& a, V2Smem& s
         mulZ = hashed ? kPrimeZ : res * res;
         hmask = hashed ? lsize - 1u : 0xffffffffu;
         tab = sg->grid[kGrid] + off;
-        vecs = sg->vectors;
-        gvec = a.seg_grads[sgi].vectors;
+        vecs = sg->vectors + 2 * l;                    // (this level's feature pair of every row)
+        gvec = a.seg_grads[sgi].vectors + 2 * l;
         gtab = a.seg_grads[sgi].grid[kGrid] + 2 * (size_t)off;
         // start the runs AT this sample: its own vertices / taps are the current ones, so the step below finds nothing to
         // flush (the accumulators are zero) and the hot path needs no "slot is empty" test
@@ -192,20 +193,20 @@ __device__ __forceinline__ void scatter_levels(const ScatterV2Args& a, V2Smem& s
       }
       uint32_t ev = 0u;
       if (!kGather) ev = sm.eg[row + j];
-      if (!hashed && (A.g >= res || B.g >= res || C.g >= res)) {   // outside a dense grid (never for samples inside the AABB)
-        scatter_sample_slow<kGather>(tab, gtab, gvec, vecs, hashed, res, lsize, A, B, C, tp, l, dO, ev);
-        continue;
+      if (!hashed && (A.g >= res || B.g >= res || C.g >= res)) {   // outside a dense grid (never for samples inside the AABB):
+        slow_mask |= 1u << j;                                       // handled after the loop, out of line (keeps the call, and
+        continue;                                                   // what it does to register allocation, out of the hot loop)
       }
       // ---- vector tap of this sample (tensor_composition.cu:37-45); a new tap pair flushes the gradient run.  The two
       // rows are fetched every step (L1 hits, issued here, consumed after the index work below): no stall on them.
       if (tp.o0 != to0 || tp.o1 != to1) {
-        red2(gvec + to0 + 2 * l, va0, va1);
-        red2(gvec + to1 + 2 * l, vb0, vb1);
+        red2(gvec + to0, va0, va1);
+        red2(gvec + to1, vb0, vb1);
         va0 = va1 = vb0 = vb1 = 0.f;
         to0 = tp.o0, to1 = tp.o1;
       }
-      const float2 tv0 = __ldg(reinterpret_cast<const float2*>(vecs + tp.o0 + 2 * l));
-      const float2 tv1 = __ldg(reinterpret_cast<const float2*>(vecs + tp.o1 + 2 * l));
+      const float2 tv0 = __ldg(reinterpret_cast<const float2*>(vecs + tp.o0));
+      const float2 tv1 = __ldg(reinterpret_cast<const float2*>(vecs + tp.o1));
       // ---- cell -> the 8 vertex indices in parity-slot order; a slot whose index changed is flushed and re-keyed
       // (two different vertices that hash to the same entry keep accumulating into one slot: same table entry anyway)
       uint32_t nidx[8];
@@ -251,8 +252,23 @@ __device__ __forceinline__ void scatter_levels(const ScatterV2Args& a, V2Smem& s
     if (gtab != nullptr) {
 #pragma unroll
       for (int q = 0; q < 8; ++q) red2(gtab + 2 * (size_t)idx[q], accx[q], accy[q]);
-      red2(gvec + to0 + 2 * l, va0, va1);
-      red2(gvec + to1 + 2 * l, vb0, vb1);
+      red2(gvec + to0, va0, va1);
+      red2(gvec + to1, vb0, vb1);
+    }
+    if (slow_mask != 0u) {   // cold: samples outside a dense level's grid, one by one with the forward's general index wrap
+      for (int j = 0; j < cnt; ++j) {
+        if (!((slow_mask >> j) & 1u)) continue;
+        const uint32_t sgi = sm.seg[tid * kV2Chunk + j];
+        const float4 p4 = sm.pos[row + j];
+        const float c0 = (kGrid == 2) ? p4.y : p4.x, c1 = (kGrid == 0 || kGrid == 1) ? p4.y : p4.z, c2 = (kGrid == 0) ? p4.z : p4.w;
+        const float cv = (kAxis == 0) ? p4.x : (kAxis == 1) ? p4.y : (kAxis == 2) ? p4.z : p4.w;
+        const hrf_segment* sg = f.segments + sgi;
+        const uint32_t off = sg->level_offset[l];
+        scatter_sample_slow<kGather>(sg->grid[kGrid] + off, a.seg_grads[sgi].grid[kGrid] + 2 * (size_t)off, a.seg_grads[sgi].vectors,
+                                     sg->vectors, ((sg->hashed_mask >> l) & 1u) != 0u, res, sg->level_size[l], to_cell(scale, c0),
+                                     to_cell(scale, c1), to_cell(scale, c2), make_tap(cv, f.vec_res, kAxis), l, sm.df[row + j],
+                                     kGather ? 0u : sm.eg[row + j]);
+      }
     }
   }
 }

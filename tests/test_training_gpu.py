@@ -209,7 +209,7 @@ def test_feature_reuse_modes_train_alike(cuda, segs):
     for reuse in ("none", "feat", "feat+grid"):
         model, frames = make_model(segs, table_std=3.0, device=cuda)      # dense enough for rays to saturate: pruning bites
         if b is None:
-            b = synthetic_rays(300, 96, frames, seed=6, ragged=True)
+            b = synthetic_rays(300, 400, frames, seed=6, ragged=True)        # long rays: they saturate, pruning removes samples
         g = {k: v.to(cuda).contiguous() for k, v in b.items() if k in ("o", "d", "frames", "t", "ri", "rgba")}
         init = [p.detach().clone() for p in model.hot_parameters()]
         tr = FusedTrainer(model, lr=1e-2, prune=True, seed=11, reuse=reuse)
