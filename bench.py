@@ -453,19 +453,34 @@ def main():
 
     host_loss = torch.zeros(64).pin_memory()
     e2e_kept = []
+    # Train: two resident device batches; batch i+1 is copied from pinned host memory on the copy stream while step i runs
+    # (the copy waits until the step that last read that buffer has finished, the step waits for its copy).
+    dev_batches = [{k: torch.empty_like(host[k], device=dev) for k in keys} for _ in range(2)]
+    copied = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def upload_into(slot):
+        with torch.cuda.stream(streams[0]):
+            streams[0].wait_event(consumed[slot])
+            for k in keys:
+                dev_batches[slot][k].copy_(host[k], non_blocking=True)
+            copied[slot].record(streams[0])
 
     def e2e_train(k):
-        nxt = upload(streams[0])
+        cur = torch.cuda.current_stream()
+        for c in consumed:
+            c.record(cur)
+        upload_into(0)
         for i in range(k):
-            bb, done = nxt
-            torch.cuda.current_stream().wait_event(done)
+            slot = i & 1
+            cur.wait_event(copied[slot])
             if i + 1 < k:
-                nxt = upload(streams[0])
+                upload_into(slot ^ 1)
+            bb = dev_batches[slot]
             trainer.step(bb["o"], bb["d"], bb["frames"], bb["t"], bb["ri"], bb["rgba"], RAYS)
+            consumed[slot].record(cur)
             host_loss[i % 64:i % 64 + 1].copy_(trainer.last["loss"].reshape(1), non_blocking=True)   # the D2H read of the step's result
             e2e_kept.append(trainer.last["samples"])
-            for v in bb.values():
-                v.record_stream(torch.cuda.current_stream())
         torch.cuda.synchronize()
 
     e2e_loop = e2e_render if args.mode == "render" else e2e_train

@@ -29,7 +29,7 @@ class SamplerParams(C.Structure):
 
 class Segment(C.Structure):
     _fields_ = [("grid", vp * 4), ("vectors", vp), ("level_offset", u32 * N_LEVELS), ("level_size", u32 * N_LEVELS),
-                ("hashed_mask", u32), ("n_entries", u32)]
+                ("hashed_mask", u32), ("n_entries", u32), ("vectors_t", vp)]
 
 
 class Field(C.Structure):
@@ -52,7 +52,7 @@ class SegmentGrads(C.Structure):
 
 class AdamTensor(C.Structure):
     _fields_ = [("param", vp), ("exp_avg", vp), ("exp_avg_sq", vp), ("grad", vp), ("shadow_bf16", vp), ("blob_perm", vp),
-                ("active", vp), ("step", vp), ("n", i64), ("first_block", i64)]
+                ("active", vp), ("step", vp), ("n", i64), ("first_block", i64), ("vectors_t", vp), ("vec_res", i32)]
 
 
 ADAM_BLOCK_ELEMS = 4096
@@ -66,7 +66,8 @@ class DpPeers(C.Structure):
 class DpTensor(C.Structure):
     _fields_ = [("param", vp), ("exp_avg", vp), ("exp_avg_sq", vp), ("grad_offset", i64), ("shadow_offset", i64),
                 ("local_shadow_bf16", vp), ("blob_perm", vp), ("active", vp), ("step", vp), ("n", i64),
-                ("shard_begin", i64), ("shard_end", i64), ("first_block", i64), ("sharded", i32)]
+                ("shard_begin", i64), ("shard_end", i64), ("first_block", i64), ("sharded", i32), ("vec_res", i32),
+                ("vectors_t", vp)]
 
 
 _SIGNATURES = {
@@ -105,6 +106,7 @@ _SIGNATURES = {
     "hrf_compose_tensors_backward": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, i64, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]),
     "hrf_adam_step": (C.c_int, [vp, vp, vp, vp, vp, i64, f32, f32, f32, f32, C.c_int, f32, vp]),
     "hrf_cast_bf16": (C.c_int, [vp, vp, i64, vp]),
+    "hrf_transpose_vectors": (C.c_int, [vp, vp, C.c_int, vp]),
     "hrf_occupancy_from_masks": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
     "hrf_occupancy_union_count": (C.c_int, [vp, vp, i64, vp, vp]),
     "hrf_selftest_umma": (C.c_int, [vp, vp, vp, C.c_int, C.c_int, C.c_int, u32, u32, u32, u32, u32, u32, u32, u32,

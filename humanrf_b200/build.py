@@ -72,11 +72,13 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     if any(rc != 0 for rc, _ in results):
         sys.stderr.write(log)
         raise RuntimeError("nvcc failed building libhumanrf_b200.so (see humanrf_b200/build.log)")
-    res = subprocess.run([nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", str(LIB),
+    tmp = LIB.with_suffix(".so.tmp")      # linked beside, then renamed: a reader never sees a half-written library
+    res = subprocess.run([nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", str(tmp),
                           *[str(OBJ / (s.stem + ".o")) for s in srcs]], capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
         raise RuntimeError("link of libhumanrf_b200.so failed")
+    os.replace(tmp, LIB)
     if verbose:
         print(log)
     STAMP.write_text(dig)

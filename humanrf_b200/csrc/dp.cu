@@ -16,6 +16,12 @@
 
 namespace hrf {
 
+__device__ __forceinline__ int64_t vectors_t_index_dp(int64_t i, int vr) {   // as vectors_t_index in train.cu
+  const int c = (int)(i & 31);
+  const int64_t row = (i >> 5) % vr, axis = (i >> 5) / vr;
+  return ((axis * 16 + (c >> 1)) * vr + row) * 2 + (c & 1);
+}
+
 struct DpPeers {
   const float* grad[HRF_DP_MAX_WORLD];
   __nv_bfloat16* shadow[HRF_DP_MAX_WORLD];
@@ -72,6 +78,10 @@ __global__ void __launch_bounds__(256) dp_reduce_adam_kernel(const DpPeers P, co
       } else if (t.local_shadow_bf16 != nullptr) {
         *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(t.local_shadow_bf16) + i) = q;
       }
+      if (t.vectors_t != nullptr) {
+        *reinterpret_cast<float2*>(t.vectors_t + vectors_t_index_dp(i, t.vec_res)) = make_float2(p.x, p.y);
+        *reinterpret_cast<float2*>(t.vectors_t + vectors_t_index_dp(i + 2, t.vec_res)) = make_float2(p.z, p.w);
+      }
     }
   } else {
     for (int64_t i = start + threadIdx.x; i < end; i += 256) {
@@ -88,6 +98,7 @@ __global__ void __launch_bounds__(256) dp_reduce_adam_kernel(const DpPeers P, co
       } else if (t.local_shadow_bf16 != nullptr) {
         reinterpret_cast<__nv_bfloat16*>(t.local_shadow_bf16)[t.blob_perm != nullptr ? (int64_t)t.blob_perm[i] : i] = q;
       }
+      if (t.vectors_t != nullptr) t.vectors_t[vectors_t_index_dp(i, t.vec_res)] = p;
     }
   }
 }

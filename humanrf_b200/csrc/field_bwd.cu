@@ -732,6 +732,12 @@ extern "C" int hrf_field_backward_mlp(const hrf_field* f, const hrf_samples* s, 
 int hrf_launch_scatter_v2(const hrf_field* f, const hrf_samples* s, const hrf_segment_grads* seg_grads, const void* grid_feat_bf16,
                           const int32_t* feat_index, int64_t grid_feat_stride, const void* workspace, int grid_first, int grid_count,
                           cudaStream_t st);   // scatter_v2.cu
+int hrf_launch_scatter_v3(const hrf_field* f, const hrf_samples* s, const hrf_segment_grads* seg_grads, const void* grid_feat_bf16,
+                          const int32_t* feat_index, int64_t grid_feat_stride, const void* workspace, int grid_first, int grid_count,
+                          cudaStream_t st);   // scatter_v3.cu
+#ifndef HRF_SCATTER_DEFAULT
+#define HRF_SCATTER_DEFAULT 1   // measured on B200 (profiles/): see DESIGN.md section 3
+#endif
 
 extern "C" int hrf_field_backward_tables(const hrf_field* f, const hrf_samples* s, const hrf_segment_grads* seg_grads,
                                          const void* grid_feat_bf16, const int32_t* feat_index, int64_t grid_feat_stride,
@@ -740,9 +746,13 @@ extern "C" int hrf_field_backward_tables(const hrf_field* f, const hrf_samples* 
   HRF_REQUIRE(grid_first >= 0 && grid_count >= 1 && grid_first + grid_count <= 4, "grids are 0..3 (xyz, xyt, yzt, xzt)");
   if (s->num_samples == 0) return 0;
   HRF_REQUIRE(workspace != nullptr, "needs the workspace hrf_field_backward_mlp filled");
-  // HRF_SCATTER_V2=0 selects the first-generation kernels below (kept for A/B and as a cross-check in the tests)
-  const bool v2 = [] { const char* e = getenv("HRF_SCATTER_V2"); return !(e && e[0] == '0'); }();   // (read per call: the tests switch it)
-  if (v2)
+  // HRF_SCATTER = 3 | 2 | 1 (read per call: the tests switch it): 3 = scatter_v3.cu, 2 = scatter_v2.cu, 1 = the
+  // first-generation kernels below.  All three stay built: each is the others' cross-check in tests/test_scatter_gpu.py.
+  const int gen = [] { const char* e = getenv("HRF_SCATTER"); const int v = e ? atoi(e) : HRF_SCATTER_DEFAULT; return (v >= 1 && v <= 3) ? v : HRF_SCATTER_DEFAULT; }();
+  if (gen == 3)
+    return hrf_launch_scatter_v3(f, s, seg_grads, grid_feat_bf16, feat_index, grid_feat_stride, workspace, grid_first, grid_count,
+                                 reinterpret_cast<cudaStream_t>(stream));
+  if (gen == 2)
     return hrf_launch_scatter_v2(f, s, seg_grads, grid_feat_bf16, feat_index, grid_feat_stride, workspace, grid_first, grid_count,
                                  reinterpret_cast<cudaStream_t>(stream));
   ScatterArgs sa;

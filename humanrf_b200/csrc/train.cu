@@ -8,6 +8,18 @@
 
 namespace hrf {
 
+// element i of a `vectors` tensor [4, VR, 32] inside its transposed copy [4, 16, VR, 2]
+__device__ __forceinline__ int64_t vectors_t_index(int64_t i, int vr) {
+  const int c = (int)(i & 31);
+  const int64_t row = (i >> 5) % vr, axis = (i >> 5) / vr;
+  return ((axis * 16 + (c >> 1)) * vr + row) * 2 + (c & 1);
+}
+
+__global__ void transpose_vectors_kernel(const float* __restrict__ v, float* __restrict__ vt, int vr) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (int64_t)4 * vr * 32) vt[vectors_t_index(i, vr)] = v[i];
+}
+
 __device__ __forceinline__ float block_sum_256(float v) {
   __shared__ float part[8];
 #pragma unroll
@@ -102,6 +114,10 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const hrf_adam_tensor* 
       *reinterpret_cast<float4*>(t.exp_avg_sq + i) = v;
       if (zero_grad) *reinterpret_cast<float4*>(t.grad + i) = make_float4(0.f, 0.f, 0.f, 0.f);
       if (sh != nullptr) *reinterpret_cast<uint2*>(sh + i) = make_uint2(pack_bf16x2(p.x, p.y), pack_bf16x2(p.z, p.w));
+      if (t.vectors_t != nullptr) {   // (i is a multiple of 4: two feature pairs = two levels of one row)
+        *reinterpret_cast<float2*>(t.vectors_t + vectors_t_index(i, t.vec_res)) = make_float2(p.x, p.y);
+        *reinterpret_cast<float2*>(t.vectors_t + vectors_t_index(i + 2, t.vec_res)) = make_float2(p.z, p.w);
+      }
     }
   } else {
     for (int64_t i = start + threadIdx.x; i < end; i += 256) {
@@ -110,6 +126,7 @@ __global__ void __launch_bounds__(256) adam_multi_kernel(const hrf_adam_tensor* 
       t.param[i] = p, t.exp_avg[i] = m, t.exp_avg_sq[i] = v;
       if (zero_grad) t.grad[i] = 0.f;
       if (sh != nullptr) sh[t.blob_perm != nullptr ? (int64_t)t.blob_perm[i] : i] = __float2bfloat16_rn(p);
+      if (t.vectors_t != nullptr) t.vectors_t[vectors_t_index(i, t.vec_res)] = p;
     }
   }
 }
@@ -125,6 +142,14 @@ extern "C" int hrf_train_loss(const float* color, const float* weights_sum, cons
   if (num_rays == 0) return 0;
   train_loss_kernel<<<(unsigned)((num_rays + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       color, weights_sum, rgba, background, num_rays, huber_delta, bce_weight, loss_scale_dev, d_color, d_weights_sum, loss_out);
+  HRF_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int hrf_transpose_vectors(const float* vectors, float* vectors_t, int vec_res, void* stream) {
+  HRF_REQUIRE(vectors != nullptr && vectors_t != nullptr && vec_res >= 1, "bad argument");
+  const int64_t n = (int64_t)4 * vec_res * 32;
+  transpose_vectors_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(vectors, vectors_t, vec_res);
   HRF_CHECK_LAUNCH();
   return 0;
 }

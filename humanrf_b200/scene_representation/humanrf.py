@@ -217,8 +217,10 @@ class _NativeField:
                 if p.device != dev or p.dtype != torch.float32 or not p.is_contiguous():
                     raise RuntimeError("humanrf_b200: parameters must be contiguous fp32 CUDA tensors on one device")
             self.shadows = []
+            self.vec_t = []     # transposed fp32 copies of `vectors`, [4][16][VR][2]: what the gradient scatter reads
             for fg in m.feature_grids:
                 self.shadows.append([torch.empty(g.numel(), dtype=torch.bfloat16, device=dev) for g in fg.grids()])
+                self.vec_t.append(torch.empty(fg.vectors.numel(), dtype=torch.float32, device=dev))
             self.blob = torch.zeros(MLP_BLOB_ELEMS, dtype=torch.bfloat16, device=dev)
             dst, src = mlp_blob_permutation(m.camera_embedding_dim)
             self.perm = (torch.from_numpy(dst).to(dev), torch.from_numpy(src).to(dev))
@@ -228,6 +230,7 @@ class _NativeField:
                 for k in range(4):
                     segs[s].grid[k] = self.shadows[s][k].data_ptr()
                 segs[s].vectors = fg.vectors.data_ptr()
+                segs[s].vectors_t = self.vec_t[s].data_ptr()
                 for l in range(16):
                     segs[s].level_offset[l] = int(lay.offset[l])
                     segs[s].level_size[l] = int(lay.size[l])
@@ -267,7 +270,10 @@ class _NativeField:
                         if old is None or old[i] != versions[i]:
                             L.check(lib.hrf_cast_bf16(g.data_ptr(), self.shadows[s][k].data_ptr(), g.numel(), L.stream()))
                         i += 1
-                    i += 1  # vectors are read as fp32 directly
+                    if old is None or old[i] != versions[i]:   # vectors: read as fp32 directly; refresh the transposed copy
+                        L.check(lib.hrf_transpose_vectors(fg.vectors.data_ptr(), self.vec_t[s].data_ptr(), fg.vectors.shape[1],
+                                                          L.stream()))
+                    i += 1
                 if old is None or old[self.n_table_params:] != versions[self.n_table_params:]:
                     self.repack_mlp()
             self.versions = versions

@@ -173,8 +173,10 @@ class FusedTrainer:
                 shadow, perm = blob_ptr, self.blob_perm.data_ptr()
             elif i == 5 * S + 1:
                 shadow, perm = blob_ptr, self.blob_perm[n_sig:].data_ptr()
+            vt, vr = (nat.vec_t[i // 5].data_ptr(), int(p.shape[1])) if (i < 5 * S and i % 5 == 4) else (None, 0)
             if p2p:
                 t = L.DpTensor()
+                t.vectors_t, t.vec_res = vt, vr
                 t.param, t.exp_avg, t.exp_avg_sq = p.data_ptr(), self.exp_avg[a:b].data_ptr(), self.exp_avg_sq[a:b].data_ptr()
                 t.grad_offset, t.n = a, b - a
                 t.blob_perm, t.active, t.step = perm, seg_flag, step_ptr
@@ -189,6 +191,7 @@ class FusedTrainer:
                 first += (t.shard_end - t.shard_begin + L.ADAM_BLOCK_ELEMS - 1) // L.ADAM_BLOCK_ELEMS
             else:
                 t = L.AdamTensor()
+                t.vectors_t, t.vec_res = vt, vr
                 t.param, t.exp_avg, t.exp_avg_sq = p.data_ptr(), self.exp_avg[a:b].data_ptr(), self.exp_avg_sq[a:b].data_ptr()
                 t.grad, t.shadow_bf16, t.blob_perm = self.grad[a:b].data_ptr(), shadow, perm
                 t.active, t.step, t.n, t.first_block = seg_flag, step_ptr, b - a, first

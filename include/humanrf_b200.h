@@ -106,6 +106,10 @@ typedef struct {
   uint32_t level_size[HRF_N_LEVELS];   /* hashmap_size of each level (entries)            */
   uint32_t hashed_mask;              /* bit l: level l uses the spatial hash             */
   uint32_t n_entries;                /* entries per grid                                 */
+  /* Optional transposed fp32 copy of `vectors`, [4 axes][16 levels][vec_res][2] (hrf_transpose_vectors; kept current by
+   * hrf_adam_multi / hrf_dp_reduce_adam through hrf_adam_tensor.vectors_t): the gradient scatter reads one level's
+   * feature pair of consecutive rows from consecutive addresses.  NULL: the scatter reads `vectors` itself. */
+  const float*    vectors_t;
 } hrf_segment;
 
 typedef struct {
@@ -281,6 +285,8 @@ int hrf_adam_step(float* param, float* exp_avg, float* exp_avg_sq, const float* 
                   int64_t n, float lr, float beta1, float beta2, float eps, int step, float grad_scale,
                   void* stream);
 int hrf_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
+/* vectors [4, vec_res, 32] -> vectors_t [4, 16, vec_res, 2] (hrf_segment.vectors_t) */
+int hrf_transpose_vectors(const float* vectors, float* vectors_t, int vec_res, void* stream);
 
 /* All parameter tensors of a model in ONE launch (the per-tensor entry point above costs one launch per tensor: 23
  * for a single segment).  tensors: device array of descriptors; a tensor whose *active flag is 0 is skipped entirely
@@ -298,6 +304,8 @@ typedef struct {
   int32_t* step;                     /* device step counter of this tensor */
   int64_t n;
   int64_t first_block;               /* exclusive prefix of ceil(n / HRF_ADAM_BLOCK_ELEMS) over the tensors */
+  float* vectors_t;                  /* `vectors` tensors only: the transposed copy to refresh (hrf_segment.vectors_t), or NULL */
+  int32_t vec_res;
 } hrf_adam_tensor;
 #define HRF_ADAM_BLOCK_ELEMS 4096
 int hrf_adam_multi(const hrf_adam_tensor* tensors /* device */, int num_tensors, int64_t total_blocks, float lr, float beta1,
@@ -336,6 +344,8 @@ typedef struct {
   int64_t shard_begin, shard_end;    /* this rank's element range; [0, n) for replicated tensors */
   int64_t first_block;               /* exclusive prefix of ceil((shard_end - shard_begin) / HRF_ADAM_BLOCK_ELEMS) */
   int32_t sharded;
+  int32_t vec_res;
+  float* vectors_t;                  /* as hrf_adam_tensor */
 } hrf_dp_tensor;
 int hrf_dp_reduce_adam(const hrf_dp_peers* peers /* host */, const hrf_dp_tensor* tensors /* device */, int num_tensors,
                        int64_t total_blocks, float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);

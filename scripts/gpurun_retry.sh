@@ -1,10 +1,13 @@
 #!/bin/bash
-# gpurun with retries while the pod answers "busy" (exit code 3: nothing charged).  usage: gpurun_retry.sh <timeout> <out file> <command...>
+# gpurun with retries while the pod answers "busy" (exit code 3: nothing charged).
+# usage: gpurun_retry.sh <timeout> <out file> [--gpus N] <command>
 T=$1; OUT=$2; shift 2
-for i in $(seq 1 40); do
-  /usr/local/graft/bin/gpurun --timeout $T -- "$@" > $OUT 2>&1
+EXTRA=()
+if [ "$1" == "--gpus" ]; then EXTRA=(--gpus "$2"); shift 2; fi
+for i in $(seq 1 60); do
+  /usr/local/graft/bin/gpurun --timeout $T "${EXTRA[@]}" -- "$@" > $OUT 2>&1
   rc=$?
   [ $rc -ne 3 ] && exit $rc
-  sleep 90
+  sleep 75
 done
 exit 3

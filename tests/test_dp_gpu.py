@@ -149,5 +149,7 @@ def test_tile_sharded_render_equals_monolithic(cuda):
         s, e, c = r.render_image_sharded(cam, rank, 3)
         assert (s, e) == shard_range(160 * 120, rank, 3)
         parts.append(c)
-    torch.testing.assert_close(torch.cat(parts), full, rtol=0, atol=0)
+    # (the compositing runs per 128-sample tile inside the field kernel: another split of the pixel range shifts the tile
+    #  borders, i.e. the summation order of a ray's weights -- float rounding, not bit identity)
+    torch.testing.assert_close(torch.cat(parts), full, rtol=0, atol=2e-6)
     assert full.abs().sum() > 0 and (full == 0).any()          # object pixels rendered, background left at 0
