@@ -736,7 +736,7 @@ int hrf_launch_scatter_v3(const hrf_field* f, const hrf_samples* s, const hrf_se
                           const int32_t* feat_index, int64_t grid_feat_stride, const void* workspace, int grid_first, int grid_count,
                           cudaStream_t st);   // scatter_v3.cu
 #ifndef HRF_SCATTER_DEFAULT
-#define HRF_SCATTER_DEFAULT 1   // measured on B200 (profiles/): see DESIGN.md section 3
+#define HRF_SCATTER_DEFAULT 3   // measured on B200 (profiles/r2d_*): v3 1.50 ms, v1 1.71, v2 1.86
 #endif
 
 extern "C" int hrf_field_backward_tables(const hrf_field* f, const hrf_samples* s, const hrf_segment_grads* seg_grads,

@@ -115,6 +115,17 @@ __device__ __forceinline__ void scatter_levels(const ScatterV3Args& a, V3Smem& s
   constexpr int kAxis = (kGrid == 0) ? 3 : (kGrid == 1) ? 2 : (kGrid == 2) ? 0 : 1;
   const int row = tid * kV3Row;
   const int cnt = min(max(valid - tid * kV3Chunk, 0), kV3Chunk);
+  // columns of this lane's 8 staging slots inside egrid: the same for every level, fetched once (per level they would
+  // be a second, dependent global load in front of every staged value: 19 % of the stall samples of the first v3 cut)
+  int32_t col8[kV3Chunk];        // (a launch covers < 2^31 samples)
+  if (!kGather) {
+    const int w0 = (tid & ~31) * kV3Chunk, lane = tid & 31;
+#pragma unroll
+    for (int r = 0; r < kV3Chunk; ++r) {
+      const int s = w0 + lane + 32 * r;
+      col8[r] = s < valid ? (a.feat_index == nullptr ? (int32_t)(base + s) : __ldg(a.feat_index + base + s)) : -1;
+    }
+  }
 #pragma unroll 1
   for (int li = 0; li < kV3Levels; ++li) {
     const int l = l0 + li;
@@ -133,10 +144,7 @@ __device__ __forceinline__ void scatter_levels(const ScatterV3Args& a, V3Smem& s
       if (!kGather) {
         const uint32_t* __restrict__ eg = a.egrid + (size_t)(4 * l + kGrid) * a.egrid_stride;
 #pragma unroll
-        for (int r = 0; r < kV3Chunk; ++r) {
-          const int s = w0 + lane + 32 * r;
-          e8[r] = s < valid ? __ldg(eg + (a.feat_index == nullptr ? base + s : (int64_t)__ldg(a.feat_index + base + s))) : 0u;
-        }
+        for (int r = 0; r < kV3Chunk; ++r) e8[r] = col8[r] >= 0 ? __ldg(eg + col8[r]) : 0u;
       }
 #pragma unroll
       for (int r = 0; r < kV3Chunk; ++r) {
@@ -163,18 +171,27 @@ __device__ __forceinline__ void scatter_levels(const ScatterV3Args& a, V3Smem& s
     uint32_t to0 = 0u, to1 = 0u;          // current tap rows of the vector axis (valid once gtab != nullptr)
     float va0 = 0.f, va1 = 0.f, vb0 = 0.f, vb1 = 0.f;
     uint32_t slow_mask = 0u;
+    // the vector rows of sample j+1 are requested during step j (software pipelining: a whole step of independent work
+    // between the load and its use; the dependent `tv1 - tv0` was the most-stalled instruction of the first cut)
+    RowTap ntp{0u, 0u, 0.f};
+    float2 ntv0 = make_float2(0.f, 0.f), ntv1 = make_float2(0.f, 0.f);
+    bool pf = false;
 
 #pragma unroll 1
     for (int j = 0; j < cnt; ++j) {
       const uint32_t sgi = sm.seg[tid * kV3Chunk + j];
-      if (sgi == 255u) continue;                       // sample without a temporal segment: no gradient
+      if (sgi == 255u) {                               // sample without a temporal segment: no gradient
+        pf = false;
+        continue;
+      }
       const float4 p4 = sm.pos[row + j];
       const float2 dO = sm.df[row + j];
       const float c0 = (kGrid == 2) ? p4.y : p4.x;
       const float c1 = (kGrid == 0 || kGrid == 1) ? p4.y : p4.z;
       const float c2 = (kGrid == 0) ? p4.z : p4.w;
       const float cv = (kAxis == 0) ? p4.x : (kAxis == 1) ? p4.y : (kAxis == 2) ? p4.z : p4.w;
-      const RowTap tp = make_row_tap(cv, f.vec_res);
+      const bool use_pf = pf && sgi == cur_sgi;
+      const RowTap tp = use_pf ? ntp : make_row_tap(cv, f.vec_res);
       const Cell A = to_cell(scale, c0), B = to_cell(scale, c1), C = to_cell(scale, c2);
       if (sgi != cur_sgi) {                             // (rare) new temporal segment: flush everything, new constants
         if (gtab != nullptr) {
@@ -221,7 +238,8 @@ __device__ __forceinline__ void scatter_levels(const ScatterV3Args& a, V3Smem& s
       if (!kGather) ev = sm.eg[row + j];
       if (!hashed && (A.g >= res || B.g >= res || C.g >= res)) {   // outside a dense grid (never for samples inside the AABB):
         slow_mask |= 1u << j;                                       // handled after the loop, out of line (keeps the call, and
-        continue;                                                   // what it does to register allocation, out of the hot loop)
+        pf = false;                                                 // what it does to register allocation, out of the hot loop)
+        continue;
       }
       // ---- vector tap of this sample (tensor_composition.cu:37-45); a new tap pair flushes the gradient run.  The two
       // rows are fetched every step (L1 hits, issued here, consumed after the index work below): no stall on them.
@@ -231,8 +249,18 @@ __device__ __forceinline__ void scatter_levels(const ScatterV3Args& a, V3Smem& s
         va0 = va1 = vb0 = vb1 = 0.f;
         to0 = tp.i0, to1 = tp.i1;
       }
-      const float2 tv0 = __ldg(reinterpret_cast<const float2*>(vecs + tp.i0 * vstride));
-      const float2 tv1 = __ldg(reinterpret_cast<const float2*>(vecs + tp.i1 * vstride));
+      float2 tv0 = ntv0, tv1 = ntv1;
+      if (!use_pf) {                                     // first sample of the thread / after a skipped sample / new segment
+        tv0 = __ldg(reinterpret_cast<const float2*>(vecs + tp.i0 * vstride));
+        tv1 = __ldg(reinterpret_cast<const float2*>(vecs + tp.i1 * vstride));
+      }
+      pf = j + 1 < cnt;
+      if (pf) {
+        const float4 pn = sm.pos[row + j + 1];
+        ntp = make_row_tap((kAxis == 0) ? pn.x : (kAxis == 1) ? pn.y : (kAxis == 2) ? pn.z : pn.w, f.vec_res);
+        ntv0 = __ldg(reinterpret_cast<const float2*>(vecs + ntp.i0 * vstride));
+        ntv1 = __ldg(reinterpret_cast<const float2*>(vecs + ntp.i1 * vstride));
+      }
       // ---- cell -> the 8 vertex indices in parity-slot order; a slot whose index changed is flushed and re-keyed
       // (two different vertices that hash to the same entry keep accumulating into one slot: same table entry anyway)
       uint32_t nidx[8];
@@ -349,8 +377,8 @@ int hrf_launch_scatter_v3(const hrf_field* f, const hrf_samples* s, const hrf_se
   const int64_t blocks = (s->num_samples + kV3Samples - 1) / kV3Samples;
   const dim3 grid((unsigned)blocks, (HRF_N_LEVELS / kV3Levels) * grid_count);
   const int smem = (int)sizeof(V3Smem);
-  // CTAs per SM: 6 (80 registers, a few spilled words) or 5 (96 registers, no spills): HRF_SCATTER_CTAS, A/B on B200 in DESIGN.md
-  const int ctas = [] { const char* e = getenv("HRF_SCATTER_CTAS"); return (e && e[0] == '5') ? 5 : 6; }();
+  // CTAs per SM: 5 (96 registers: the prefetch registers and the 8 staging columns fit) or 6 (80 registers): HRF_SCATTER_CTAS
+  const int ctas = [] { const char* e = getenv("HRF_SCATTER_CTAS"); return (e && e[0] == '6') ? 6 : 5; }();
   if (grid_feat_bf16 != nullptr) {
     if (ctas == 5) grid_scatter_v3_kernel<false, 5><<<grid, kV3Threads, smem, st>>>(a);
     else grid_scatter_v3_kernel<false, 6><<<grid, kV3Threads, smem, st>>>(a);
