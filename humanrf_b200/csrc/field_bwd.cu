@@ -547,6 +547,15 @@ __global__ void __launch_bounds__(kTile, 2) field_backward_kernel(const __grid_c
     } else {
       encode_to_smem<false, kLevelUnroll>(f, s, sm.feat, tid);
     }
+    // Everything else this tile will read from global memory is requested here, before the ten MMA rounds: each round
+    // ends in asm statements that clobber memory, so the compiler cannot move a later load above them, and at 8 warps
+    // per SM a load issued where its value is needed is a fully exposed round trip.
+    const View vw = load_view(f, args.s, i, n);
+    float up_sigma = 0.f, up_rgb[3] = {0.f, 0.f, 0.f};
+    if (valid) {
+      if (args.d_sigma != nullptr) up_sigma = __ldg(args.d_sigma + i);
+      if (args.d_rgb != nullptr) up_rgb[0] = __ldg(args.d_rgb + 3 * i), up_rgb[1] = __ldg(args.d_rgb + 3 * i + 1), up_rgb[2] = __ldg(args.d_rgb + 3 * i + 2);
+    }
     if (!weights_ready) {
       mbar_wait(&sm.bar_w, 0);
       weights_ready = true;
@@ -559,7 +568,6 @@ __global__ void __launch_bounds__(kTile, 2) field_backward_kernel(const __grid_c
     mma_round(sm, phase, [&] { issue_layer(tm + kColWork, a_hs, wbase + kWSig2, 16, 64); });
     tmem_ld16(trow + kColWork, o);
     const float h0 = o[0];
-    const View vw = load_view(f, args.s, i, n);
     write_color_input(f, sm.cin, roff, vw, o);
     const int K1 = f.color_in_width;
     mma_round(sm, phase, [&] { issue_layer(tm + kColWork, a_cin, wbase + kWCol1, 64, K1); });
@@ -578,7 +586,7 @@ __global__ void __launch_bounds__(kTile, 2) field_backward_kernel(const __grid_c
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           const float r = 1.f / (1.f + __expf(-o[c]));
-          d3[c] = args.d_rgb[3 * i + c] * r * (1.f - r);
+          d3[c] = up_rgb[c] * r * (1.f - r);
         }
       }
       *reinterpret_cast<uint4*>(sm.g3 + 0 * kAChunk + roff) =
@@ -619,7 +627,7 @@ __global__ void __launch_bounds__(kTile, 2) field_backward_kernel(const __grid_c
       }
       float dh0 = 0.f;
       if (valid && args.d_sigma != nullptr)
-        dh0 = args.d_sigma[i] * f.density_scale * __expf(fminf(fmaxf(h0, -15.f), 15.f));
+        dh0 = up_sigma * f.density_scale * __expf(fminf(fmaxf(h0, -15.f), 15.f));
       *reinterpret_cast<uint4*>(sm.gs + 0 * kAChunk + roff) = make_uint4(
           pack_bf16x2(dh0, dc[16]), pack_bf16x2(dc[17], dc[18]), pack_bf16x2(dc[19], dc[20]), pack_bf16x2(dc[21], dc[22]));
       *reinterpret_cast<uint4*>(sm.gs + 1 * kAChunk + roff) = make_uint4(

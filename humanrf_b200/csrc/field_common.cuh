@@ -230,6 +230,30 @@ __device__ __forceinline__ float2 lerp_tap(const float* __restrict__ vec, const 
   return make_float2(v0.x + t.frac * (v1.x - v0.x), v0.y + t.frac * (v1.y - v0.y));
 }
 
+// The same taps as row indices, and their lerp through the TRANSPOSED copy vectors_t[axis][level][row][2] when the segment
+// has one (hrf_segment.vectors_t): the lanes of a warp are consecutive samples of a ray, i.e. neighbouring rows -- in
+// `vectors` ([axis][row][32]) every row is its own 128-byte line (15-26 lines per load instruction at the finest
+// resolution), in the transposed copy 16 rows share a line.  Same fp32 values, same arithmetic.
+struct RowTap2 {
+  uint32_t i0, i1;
+  float frac;
+};
+__device__ __forceinline__ RowTap2 make_row_tap2(float coord, int vec_res) {
+  const float c = __fmaf_rn(coord, (float)vec_res, -0.5f);
+  const float fl = floorf(c);
+  RowTap2 t;
+  t.frac = c - fl;
+  t.i0 = (uint32_t)min(max((int)fmaxf(fl, 0.f), 0), vec_res - 1);
+  t.i1 = (uint32_t)min(max((int)fminf(fl + 1.f, (float)(vec_res - 1)), 0), vec_res - 1);
+  return t;
+}
+// base = vectors_t + (axis*16 + level) * vec_res * 2  (stride 2)   or   vectors + axis * vec_res * 32 + 2 * level  (stride 32)
+__device__ __forceinline__ float2 lerp_row_tap(const float* __restrict__ base, uint32_t stride, const RowTap2& t) {
+  const float2 v0 = __ldg(reinterpret_cast<const float2*>(base + t.i0 * stride));
+  const float2 v1 = __ldg(reinterpret_cast<const float2*>(base + t.i1 * stride));
+  return make_float2(v0.x + t.frac * (v1.x - v0.x), v0.y + t.frac * (v1.y - v0.y));
+}
+
 // Degree-4 real spherical harmonics of the view direction (tcnn SphericalHarmonics on (d+1)/2).
 __device__ __forceinline__ void sh4(float dx, float dy, float dz, float* o) {
   const float x = ((dx + 1.f) * 0.5f) * 2.f - 1.f, y = ((dy + 1.f) * 0.5f) * 2.f - 1.f,
@@ -304,10 +328,14 @@ __device__ __forceinline__ void encode_to_smem(const hrf_field& f, const Sample&
   const uint32_t* g1 = sg->grid[1];
   const uint32_t* g2 = sg->grid[2];
   const uint32_t* g3 = sg->grid[3];
-  const float* vec = sg->vectors;
   const uint32_t hmask = sg->hashed_mask;
-  const VecTap tx = make_tap(s.x, f.vec_res, 0), ty = make_tap(s.y, f.vec_res, 1), tz = make_tap(s.z, f.vec_res, 2),
-               tt = make_tap(s.t, f.vec_res, 3);
+  const RowTap2 tx = make_row_tap2(s.x, f.vec_res), ty = make_row_tap2(s.y, f.vec_res), tz = make_row_tap2(s.z, f.vec_res),
+                tt = make_row_tap2(s.t, f.vec_res);
+  const bool vt = sg->vectors_t != nullptr;
+  const float* vbase = vt ? sg->vectors_t : sg->vectors;
+  const uint32_t vstride = vt ? 2u : (uint32_t)HRF_N_FEATURES;
+  const uint32_t vaxis = (uint32_t)f.vec_res * (vt ? 2u * HRF_N_LEVELS : (uint32_t)HRF_N_FEATURES);   // elements per axis
+  const uint32_t vlevel = vt ? 2u * (uint32_t)f.vec_res : 2u;                                            // elements per level
   auto one_level = [&](int l) -> uint32_t {
     const float scale = f.level_scale[l];
     const uint32_t res = f.level_res[l];
@@ -320,11 +348,12 @@ __device__ __forceinline__ void encode_to_smem(const hrf_field& f, const Sample&
     const float2 e1 = gather_level(g1 + off, hashed, res, size, cx, cy, ct);
     const float2 e2 = gather_level(g2 + off, hashed, res, size, cy, cz, ct);
     const float2 e3 = gather_level(g3 + off, hashed, res, size, cx, cz, ct);
-    const float2 vx = lerp_tap(vec, tx, 2 * l), vy = lerp_tap(vec, ty, 2 * l), vz = lerp_tap(vec, tz, 2 * l),
-                 vt = lerp_tap(vec, tt, 2 * l);
+    const float* vl = vbase + (uint32_t)l * vlevel;
+    const float2 vx = lerp_row_tap(vl, vstride, tx), vy = lerp_row_tap(vl + vaxis, vstride, ty),
+                 vz = lerp_row_tap(vl + 2u * vaxis, vstride, tz), vt_ = lerp_row_tap(vl + 3u * vaxis, vstride, tt);
     // tensor_composition.cu:49-52 : xyz*v_t + xyt*v_z + yzt*v_x + xzt*v_y
-    const float o0 = e0.x * vt.x + e1.x * vz.x + e2.x * vx.x + e3.x * vy.x;
-    const float o1 = e0.y * vt.y + e1.y * vz.y + e2.y * vx.y + e3.y * vy.y;
+    const float o0 = e0.x * vt_.x + e1.x * vz.x + e2.x * vx.x + e3.x * vy.x;
+    const float o1 = e0.y * vt_.y + e1.y * vz.y + e2.y * vx.y + e3.y * vy.y;
     if (kSaveGrid && egrid != nullptr) {
       uint32_t* eg = egrid + (size_t)(4 * l) * n + i;
       eg[0] = pack_bf16x2(e0.x, e0.y);
