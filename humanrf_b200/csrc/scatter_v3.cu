@@ -32,19 +32,12 @@ struct ScatterV3Args {
   int grid_first, grid_count;
 };
 
-constexpr int kV3SegCache = 8;   // temporal segments whose descriptors are cached in shared memory (more: read from global)
 struct __align__(16) V3Smem {
   float4 pos[kV3Threads * kV3Row];
-  float2 df[2][kV3Threads * kV3Row];   // double buffer: level l+1 lands (cp.async) while level l is walked
+  float2 df[kV3Threads * kV3Row];
   uint32_t eg[kV3Threads * kV3Row];
   uint8_t seg[kV3Samples];
-  hrf_segment segd[kV3SegCache];
-  hrf_segment_grads segg[kV3SegCache];
 };
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 __device__ __forceinline__ void red2(float* addr, float a, float b) {
   // (no "memory" clobber: the gradient buffers are never read in this kernel, and the clobber would pin every load of
@@ -133,40 +126,34 @@ __device__ __forceinline__ void scatter_levels(const ScatterV3Args& a, V3Smem& s
       col8[r] = s < valid ? (a.feat_index == nullptr ? (int32_t)(base + s) : __ldg(a.feat_index + base + s)) : -1;
     }
   }
-  // d(composed features) of one level for the warp's 256 samples -> buffer `buf`, asynchronously (cp.async, 8 per lane)
-  auto issue_df = [&](int l, int buf) {
-    const int w0 = (tid & ~31) * kV3Chunk, lane = tid & 31;
-    const float2* __restrict__ dfl = a.dfeat + (size_t)l * ns + base;
-#pragma unroll
-    for (int r = 0; r < kV3Chunk; ++r) {
-      const int s = w0 + lane + 32 * r;
-      float2* dst = &sm.df[buf][(s >> 3) * kV3Row + (s & 7)];
-      if (s < valid) cp_async8(dst, dfl + s);
-      else *dst = make_float2(0.f, 0.f);
-    }
-  };
-  issue_df(l0, 0);
 #pragma unroll 1
   for (int li = 0; li < kV3Levels; ++li) {
     const int l = l0 + li;
-    const int buf = li & 1;
-    __syncwarp();  // this warp's lanes are done with the previous level's eg (and with df[buf ^ 1], two levels back)
-    if (!kGather) {
-      // per-grid features of this level for the warp's 256 samples (8 coalesced loads per lane)
+    __syncwarp();  // this warp's lanes are done with the previous level's df / eg
+    {
+      // the warp stages the 256 samples its own lanes walk (rows of threads 32w .. 32w+31): 8 coalesced loads per lane
       const int w0 = (tid & ~31) * kV3Chunk, lane = tid & 31;
-      const uint32_t* __restrict__ eg = a.egrid + (size_t)(4 * l + kGrid) * a.egrid_stride;
-      uint32_t e8[kV3Chunk];
-#pragma unroll
-      for (int r = 0; r < kV3Chunk; ++r) e8[r] = col8[r] >= 0 ? __ldg(eg + col8[r]) : 0u;
+      const float2* __restrict__ dfl = a.dfeat + (size_t)l * ns + base;
+      float2 d8[kV3Chunk];
 #pragma unroll
       for (int r = 0; r < kV3Chunk; ++r) {
         const int s = w0 + lane + 32 * r;
-        sm.eg[(s >> 3) * kV3Row + (s & 7)] = e8[r];
+        d8[r] = s < valid ? __ldg(dfl + s) : make_float2(0.f, 0.f);
+      }
+      uint32_t e8[kV3Chunk];
+      if (!kGather) {
+        const uint32_t* __restrict__ eg = a.egrid + (size_t)(4 * l + kGrid) * a.egrid_stride;
+#pragma unroll
+        for (int r = 0; r < kV3Chunk; ++r) e8[r] = col8[r] >= 0 ? __ldg(eg + col8[r]) : 0u;
+      }
+#pragma unroll
+      for (int r = 0; r < kV3Chunk; ++r) {
+        const int s = w0 + lane + 32 * r;
+        sm.df[(s >> 3) * kV3Row + (s & 7)] = d8[r];
+        if (!kGather) sm.eg[(s >> 3) * kV3Row + (s & 7)] = e8[r];
       }
     }
-    cp_async_wait_all();   // df[buf] of this level has landed
     __syncwarp();
-    if (li + 1 < kV3Levels) issue_df(l + 1, buf ^ 1);   // the next level's df travels while this level is walked
     const float scale = f.level_scale[l];
     const uint32_t res = f.level_res[l];
 
@@ -198,7 +185,7 @@ __device__ __forceinline__ void scatter_levels(const ScatterV3Args& a, V3Smem& s
         continue;
       }
       const float4 p4 = sm.pos[row + j];
-      const float2 dO = sm.df[buf][row + j];
+      const float2 dO = sm.df[row + j];
       const float c0 = (kGrid == 2) ? p4.y : p4.x;
       const float c1 = (kGrid == 0 || kGrid == 1) ? p4.y : p4.z;
       const float c2 = (kGrid == 0) ? p4.z : p4.w;
@@ -217,8 +204,7 @@ __device__ __forceinline__ void scatter_levels(const ScatterV3Args& a, V3Smem& s
           red2(gvec + to1 * HRF_N_FEATURES, vb0, vb1);
           va0 = va1 = vb0 = vb1 = 0.f;
         }
-        const hrf_segment* sg = sgi < (uint32_t)kV3SegCache ? &sm.segd[sgi] : f.segments + sgi;     // (cached at kernel start)
-        const hrf_segment_grads* gg = sgi < (uint32_t)kV3SegCache ? &sm.segg[sgi] : a.seg_grads + sgi;
+        const hrf_segment* sg = f.segments + sgi;
         const uint32_t off = sg->level_offset[l];
         lsize = sg->level_size[l];
         hashed = ((sg->hashed_mask >> l) & 1u) != 0u;
@@ -231,8 +217,8 @@ __device__ __forceinline__ void scatter_levels(const ScatterV3Args& a, V3Smem& s
         vstride = sg->vectors_t != nullptr ? 2u : (uint32_t)HRF_N_FEATURES;
         vecs = sg->vectors_t != nullptr ? sg->vectors_t + (size_t)(kAxis * HRF_N_LEVELS + l) * f.vec_res * 2
                                         : sg->vectors + (size_t)kAxis * f.vec_res * HRF_N_FEATURES + 2 * l;
-        gvec = gg->vectors + (size_t)kAxis * f.vec_res * HRF_N_FEATURES + 2 * l;
-        gtab = gg->grid[kGrid] + 2 * (size_t)off;
+        gvec = a.seg_grads[sgi].vectors + (size_t)kAxis * f.vec_res * HRF_N_FEATURES + 2 * l;
+        gtab = a.seg_grads[sgi].grid[kGrid] + 2 * (size_t)off;
         // start the runs AT this sample: its own vertices / taps are the current ones, so the step below finds nothing to
         // flush (the accumulators are zero) and the hot path needs no "slot is empty" test
         to0 = tp.i0, to1 = tp.i1;
@@ -334,7 +320,7 @@ __device__ __forceinline__ void scatter_levels(const ScatterV3Args& a, V3Smem& s
         const uint32_t off = sg->level_offset[l];
         scatter_sample_slow<kGather>(sg->grid[kGrid] + off, a.seg_grads[sgi].grid[kGrid] + 2 * (size_t)off, a.seg_grads[sgi].vectors,
                                      sg->vectors, ((sg->hashed_mask >> l) & 1u) != 0u, res, sg->level_size[l], to_cell(scale, c0),
-                                     to_cell(scale, c1), to_cell(scale, c2), make_tap(cv, f.vec_res, kAxis), l, sm.df[buf][row + j],
+                                     to_cell(scale, c1), to_cell(scale, c2), make_tap(cv, f.vec_res, kAxis), l, sm.df[row + j],
                                      kGather ? 0u : sm.eg[row + j]);
       }
     }
@@ -352,17 +338,7 @@ __global__ void __launch_bounds__(kV3Threads, kCtas) grid_scatter_v3_kernel(cons
   const int k = a.grid_first + (int)blockIdx.y % a.grid_count;
   const int l0 = ((int)blockIdx.y / a.grid_count) * kV3Levels;
   const int valid = (int)((n - base) < kV3Samples ? (n - base) : kV3Samples);
-  {   // the descriptors of the first kV3SegCache temporal segments: every level of every thread reads them again
-    const int nseg = a.f.num_segments < kV3SegCache ? a.f.num_segments : kV3SegCache;
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(a.f.segments);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(sm.segd);
-    for (int i = tid; i < nseg * (int)(sizeof(hrf_segment) / 4); i += kV3Threads) dst[i] = __ldg(src + i);
-    const uint32_t* gsrc = reinterpret_cast<const uint32_t*>(a.seg_grads);
-    uint32_t* gdst = reinterpret_cast<uint32_t*>(sm.segg);
-    for (int i = tid; i < nseg * (int)(sizeof(hrf_segment_grads) / 4); i += kV3Threads) gdst[i] = __ldg(gsrc + i);
-    __syncthreads();   // (the only block-wide barrier of the kernel)
-  }
-  {   // positions / segment ids of the 256 samples this warp's lanes walk (warp-private: no block barrier after this point)
+  {   // positions / segment ids of the 256 samples this warp's lanes walk (warp-private: no block barrier anywhere)
     const int w0 = (tid & ~31) * kV3Chunk, lane = tid & 31;
 #pragma unroll
     for (int r = 0; r < kV3Chunk; ++r) {
@@ -401,7 +377,6 @@ int hrf_launch_scatter_v3(const hrf_field* f, const hrf_samples* s, const hrf_se
   const int64_t blocks = (s->num_samples + kV3Samples - 1) / kV3Samples;
   const dim3 grid((unsigned)blocks, (HRF_N_LEVELS / kV3Levels) * grid_count);
   const int smem = (int)sizeof(V3Smem);
-  static_assert(sizeof(V3Smem) <= 45 * 1024, "5 CTAs of the v3 scatter must fit the 227 KB of shared memory of an SM");
   // CTAs per SM: 5 (96 registers: the prefetch registers and the 8 staging columns fit) or 6 (80 registers): HRF_SCATTER_CTAS
   const int ctas = [] { const char* e = getenv("HRF_SCATTER_CTAS"); return (e && e[0] == '6') ? 6 : 5; }();
   if (grid_feat_bf16 != nullptr) {
