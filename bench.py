@@ -351,7 +351,8 @@ def main():
         # model).  1e-6 keeps the model at its initial statistics; the optimiser does exactly the same work for any lr.
         trainer = FusedTrainer(model, lr=float(os.environ.get("HRF_BENCH_LR", "1e-6")), world_size=world,
                                reuse=os.environ.get("HRF_TRAIN_REUSE", "feat+grid"),
-                               exchange=os.environ.get("HRF_TRAIN_EXCHANGE", "p2p"))
+                               exchange=os.environ.get("HRF_TRAIN_EXCHANGE", "p2p"),
+                               overlap_exchange=os.environ.get("HRF_DP_OVERLAP", "1") != "0")
         trainer.profile = True
     g = {k: v.to(dev).contiguous() for k, v in b.items() if k in ("o", "d", "frames", "t", "ri", "rgba")}
     n = g["t"].shape[0]
@@ -549,9 +550,12 @@ def main():
             line["phases_ms"] = phases          # CUDA events inside FusedTrainer.step, mean over the timed steps, max over ranks
             if world > 1:
                 line["allreduce_ms"] = phases.get("exchange+adam")
-                line["exchange"] = {"kind": trainer.exchange, "ms": phases.get("exchange+adam"),
-                                    "note": "barrier + fused reduce-scatter/Adam/shadow all-gather kernel over NVLink peer memory + "
-                                            "barrier + bucket memset; replaces the single-GPU Adam (see phases_ms at N=1)"}
+                line["exchange"] = {"kind": trainer.exchange, "overlapped_with_scatter": trainer.overlap_exchange,
+                                    "exposed_ms": phases.get("exchange+adam"),
+                                    "note": "fused reduce-scatter/Adam/shadow all-gather kernel over NVLink peer memory between two "
+                                            "barriers, one launch per hash grid on a side stream while the next grid is scattered; "
+                                            "exposed_ms = what is left after the last scatter launch; replaces the single-GPU Adam "
+                                            "(see phases_ms at N=1)"}
         if world == 1 and not args.no_cpu_baseline:
             v, cores, sample, _ = cpu_oracle_rate(args.mode, steps=2, warmup=1, budget_s=20.0)
             line["cpu_baseline"] = {"value": v, "unit": "rays/s", "cores": cores, "kind": "port", "sample": sample}

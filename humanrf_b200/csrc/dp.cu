@@ -30,9 +30,10 @@ struct DpPeers {
 
 template <int kWorld>
 __global__ void __launch_bounds__(256) dp_reduce_adam_kernel(const DpPeers P, const hrf_dp_tensor* __restrict__ T, int num,
-                                                             float lr, float b1, float b2, float eps, float gscale) {
+                                                             int64_t block_first, float lr, float b1, float b2, float eps,
+                                                             float gscale) {
   int lo = 0, hi = num - 1;
-  const int64_t b = blockIdx.x;
+  const int64_t b = block_first + blockIdx.x;
   while (lo < hi) {
     const int mid = (lo + hi + 1) >> 1;
     if (T[mid].first_block <= b) lo = mid;
@@ -143,13 +144,14 @@ extern "C" int hrf_peer_close(void* ptr) {
 }
 
 extern "C" int hrf_dp_reduce_adam(const hrf_dp_peers* peers, const hrf_dp_tensor* tensors, int num_tensors,
-                                  int64_t total_blocks, float lr, float beta1, float beta2, float eps, float grad_scale,
-                                  void* stream) {
+                                  int64_t block_first, int64_t block_count, int advance_steps, float lr, float beta1,
+                                  float beta2, float eps, float grad_scale, void* stream) {
+  const int64_t total_blocks = block_count;
   HRF_REQUIRE(peers != nullptr && tensors != nullptr && num_tensors >= 1, "null argument");
   HRF_REQUIRE(peers->world >= 1 && peers->world <= HRF_DP_MAX_WORLD && peers->rank >= 0 && peers->rank < peers->world,
               "world size must be 1..8 (one NVSwitch domain)");
-  if (total_blocks == 0) return 0;
-  HRF_REQUIRE(total_blocks < (1ll << 31), "too many blocks");
+  HRF_REQUIRE(block_first >= 0 && total_blocks >= 0 && total_blocks < (1ll << 31), "bad block range");
+  if (total_blocks == 0 && !advance_steps) return 0;
   DpPeers P;
   for (int r = 0; r < HRF_DP_MAX_WORLD; ++r) {
     P.grad[r] = r < peers->world ? peers->grad[r] : nullptr;
@@ -158,18 +160,21 @@ extern "C" int hrf_dp_reduce_adam(const hrf_dp_peers* peers, const hrf_dp_tensor
   }
   P.world = peers->world, P.rank = peers->rank;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  dp_steps_kernel<<<(num_tensors + 127) / 128, 128, 0, st>>>(tensors, num_tensors);
-  HRF_CHECK_LAUNCH();
+  if (advance_steps) {
+    dp_steps_kernel<<<(num_tensors + 127) / 128, 128, 0, st>>>(tensors, num_tensors);
+    HRF_CHECK_LAUNCH();
+  }
   const unsigned grid = (unsigned)total_blocks;
+  if (grid == 0) return 0;
   switch (peers->world) {
-    case 1: dp_reduce_adam_kernel<1><<<grid, 256, 0, st>>>(P, tensors, num_tensors, lr, beta1, beta2, eps, grad_scale); break;
-    case 2: dp_reduce_adam_kernel<2><<<grid, 256, 0, st>>>(P, tensors, num_tensors, lr, beta1, beta2, eps, grad_scale); break;
-    case 3: dp_reduce_adam_kernel<3><<<grid, 256, 0, st>>>(P, tensors, num_tensors, lr, beta1, beta2, eps, grad_scale); break;
-    case 4: dp_reduce_adam_kernel<4><<<grid, 256, 0, st>>>(P, tensors, num_tensors, lr, beta1, beta2, eps, grad_scale); break;
-    case 5: dp_reduce_adam_kernel<5><<<grid, 256, 0, st>>>(P, tensors, num_tensors, lr, beta1, beta2, eps, grad_scale); break;
-    case 6: dp_reduce_adam_kernel<6><<<grid, 256, 0, st>>>(P, tensors, num_tensors, lr, beta1, beta2, eps, grad_scale); break;
-    case 7: dp_reduce_adam_kernel<7><<<grid, 256, 0, st>>>(P, tensors, num_tensors, lr, beta1, beta2, eps, grad_scale); break;
-    default: dp_reduce_adam_kernel<8><<<grid, 256, 0, st>>>(P, tensors, num_tensors, lr, beta1, beta2, eps, grad_scale); break;
+    case 1: dp_reduce_adam_kernel<1><<<grid, 256, 0, st>>>(P, tensors, num_tensors, block_first, lr, beta1, beta2, eps, grad_scale); break;
+    case 2: dp_reduce_adam_kernel<2><<<grid, 256, 0, st>>>(P, tensors, num_tensors, block_first, lr, beta1, beta2, eps, grad_scale); break;
+    case 3: dp_reduce_adam_kernel<3><<<grid, 256, 0, st>>>(P, tensors, num_tensors, block_first, lr, beta1, beta2, eps, grad_scale); break;
+    case 4: dp_reduce_adam_kernel<4><<<grid, 256, 0, st>>>(P, tensors, num_tensors, block_first, lr, beta1, beta2, eps, grad_scale); break;
+    case 5: dp_reduce_adam_kernel<5><<<grid, 256, 0, st>>>(P, tensors, num_tensors, block_first, lr, beta1, beta2, eps, grad_scale); break;
+    case 6: dp_reduce_adam_kernel<6><<<grid, 256, 0, st>>>(P, tensors, num_tensors, block_first, lr, beta1, beta2, eps, grad_scale); break;
+    case 7: dp_reduce_adam_kernel<7><<<grid, 256, 0, st>>>(P, tensors, num_tensors, block_first, lr, beta1, beta2, eps, grad_scale); break;
+    default: dp_reduce_adam_kernel<8><<<grid, 256, 0, st>>>(P, tensors, num_tensors, block_first, lr, beta1, beta2, eps, grad_scale); break;
   }
   HRF_CHECK_LAUNCH();
   return 0;

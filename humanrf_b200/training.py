@@ -34,7 +34,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib as L
-from .parallel import active_segments, grid_major_bucket_layout, shard_bounds, union_batch_loss_scale
+from .parallel import active_segments, grid_major_bucket_layout, shard_bounds
 from .scene_representation.grid_layout import MLP_SIGMA_PARAMS, mlp_blob_permutation
 from .scene_representation.humanrf import HumanRF
 from .volume_rendering import ray_offsets
@@ -56,7 +56,7 @@ class FusedTrainer:
     def __init__(self, model: HumanRF, lr: float = 1e-2, betas=(0.9, 0.99), eps: float = 1e-15, lr_decay: float = 0.5,
                  max_steps: int = 50001, bce_loss_weight: float = 1e-3, huber_delta: float = 0.01,
                  render_step_size: float = 4e-4, world_size: int = 1, process_group=None, prune: bool = True,
-                 seed: int = 123, reuse: str = "feat", exchange: str = "p2p", overlap_allreduce=None):
+                 seed: int = 123, reuse: str = "feat", exchange: str = "p2p", overlap_exchange: bool = True):
         if reuse not in ("none", "feat", "feat+grid"):
             raise ValueError("reuse must be 'none', 'feat' or 'feat+grid'")
         if exchange not in ("p2p", "nccl"):
@@ -66,6 +66,9 @@ class FusedTrainer:
         self.bce_w, self.delta, self.step_size = bce_loss_weight, huber_delta, render_step_size
         self.world, self.pg, self.prune, self.reuse = world_size, process_group, prune, reuse
         self.exchange = exchange if world_size > 1 else "local"
+        # exchange="p2p": run the exchange of hash grid k (barrier + reduce/Adam/shadow kernel on a side stream) while grid
+        # k+1 is still being scattered; only the last grid's share, the small tensors and the closing barrier stay exposed
+        self.overlap_exchange = bool(overlap_exchange) and self.exchange == "p2p"
         self.rank = dist.get_rank(process_group) if world_size > 1 else 0
         self.params: List[torch.nn.Parameter] = model.hot_parameters()
         dev = self.params[0].device
@@ -109,7 +112,8 @@ class FusedTrainer:
         self.profile = False
         self.keep_grad = False       # tests: leave the step's gradient in self.grad (cleared before the next backward instead)
         if self.world > 1:
-            self._bar = torch.zeros(1 + S, dtype=torch.float32, device=dev)
+            self._bar = torch.zeros(1, dtype=torch.float32, device=dev)
+            self._side = torch.cuda.Stream(dev)
 
     # ---------------------------------------------------------------------------------------------- set-up
     def _peer_buffer(self, nbytes: int) -> torch.Tensor:
@@ -199,6 +203,11 @@ class FusedTrainer:
             items.append(t)
         self.adam_desc = _device_struct_array(items, self.dev)
         self.adam_blocks = int(first)
+        # block ranges of the 5 bucket regions (grid 0..3 of every segment, then vectors / MLPs / embeddings) in the
+        # descriptor table's block numbering: what one launch of the per-grid exchange covers
+        firsts = [int(t.first_block) for t in items] + [int(first)]
+        bounds = [firsts[k * S] for k in range(4)] + [firsts[4 * S], int(first)]
+        self.region_blocks = [(bounds[k], bounds[k + 1] - bounds[k]) for k in range(5)]
         if p2p:
             self.peers = L.DpPeers()
             for r in range(self.world):
@@ -254,15 +263,27 @@ class FusedTrainer:
         cams = cameras if self.model.camera_embedding_dim > 0 else None
         # Segments this batch touches (humanrf.py:162-179): the reference gives the others no gradient, so Adam leaves
         # their parameters, moments and step counters alone.  Decided AND consumed on the device.
+        used = None
         if S > 1:
             used = active_segments(self.model.frame_numbers_to_segment_numbers, frames, S)
             if self.world == 1:
                 self.active_dev.copy_(used)
             launches += 8
         loss_scale = None
-        if self.world > 1:                              # this rank's share of the union batch (humanrf_b200/parallel.py)
-            loss_scale = union_batch_loss_scale(num_rays, dev, self.pg).reshape(1).float().contiguous()
-            launches += 2
+        if self.world > 1:
+            # ONE small all-reduce at the head of the step: the union batch's ray count (each rank weights its loss with
+            # world * R_local / R_total so that the summed gradients are those of the union-batch mean,
+            # humanrf_b200/parallel.py) and the union of the active-segment flags (a segment takes part iff ANY rank's batch
+            # touches it).  Everything stays on the device.
+            head = torch.zeros(1 + S, dtype=torch.float32, device=dev)
+            head[0] = float(num_rays)
+            if used is not None:
+                head[1:] = used.float()
+            dist.all_reduce(head, group=self.pg)
+            loss_scale = (float(self.world * num_rays) / head[:1].clamp(min=1.0)).contiguous()
+            if used is not None:
+                self.active_dev.copy_(head[1:] > 0)
+            launches += 6
         src = feat_src = None
         n_cap = t.shape[0]
         count = None
@@ -330,20 +351,23 @@ class FusedTrainer:
                                            feat.data_ptr(), L.ptr(src), self.mlp_grad.data_ptr(), L.ptr(self.emb_grad),
                                            ws.data_ptr(), L.stream()))
         mark("backward_mlp")
-        L.check(lib.hrf_field_backward_tables(C.byref(nat.field), C.byref(samples), self.sg_dev.data_ptr(), egrid, L.ptr(src),
-                                              egrid_stride, ws.data_ptr(), 0, 4, L.stream()))
-        launches += 8
-        if bwd_events is not None:
-            bwd_events[1].record()
-        mark("scatter")
-        launches += self._exchange_and_adam(used if S > 1 else None)
-        mark("exchange+adam")
+        if self.overlap_exchange:
+            launches += self._scatter_and_exchange_overlapped(nat, samples, egrid, src, egrid_stride, ws, mark)
+        else:
+            L.check(lib.hrf_field_backward_tables(C.byref(nat.field), C.byref(samples), self.sg_dev.data_ptr(), egrid, L.ptr(src),
+                                                  egrid_stride, ws.data_ptr(), 0, 4, L.stream()))
+            launches += 8
+            if bwd_events is not None:
+                bwd_events[1].record()
+            mark("scatter")
+            launches += self._exchange_and_adam()
+            mark("exchange+adam")
         self.last = {"samples": count[0] if count is not None else n_cap, "loss": loss[0], "marks": marks}
         if return_loss:
             return float(loss.item())
         return launches
 
-    def _exchange_and_adam(self, used) -> int:
+    def _exchange_and_adam(self) -> int:
         lib = L.lib()
         lr = self.current_lr()
         self.t += 1
@@ -352,25 +376,54 @@ class FusedTrainer:
             L.check(lib.hrf_adam_multi(self.adam_desc.data_ptr(), len(self.params), self.adam_blocks, lr, b1, b2, self.eps, 1.0,
                                        0 if self.keep_grad else 1, L.stream()))
             return 2
-        S = self.model.num_segments
-        # barrier A (all ranks' gradients are complete) carrying the union of the active-segment flags
-        self._bar.zero_()
-        if used is not None:
-            self._bar[1:] = used.float()
-        dist.all_reduce(self._bar, group=self.pg)
-        if used is not None:
-            self.active_dev.copy_(self._bar[1:] > 0)
         if self.exchange == "nccl":
             dist.all_reduce(self.grad, group=self.pg)
             L.check(lib.hrf_adam_multi(self.adam_desc.data_ptr(), len(self.params), self.adam_blocks, lr, b1, b2, self.eps,
                                        1.0 / self.world, 1, L.stream()))
-            return 6
-        L.check(lib.hrf_dp_reduce_adam(C.byref(self.peers), self.adam_desc.data_ptr(), len(self.params), self.adam_blocks, lr, b1,
-                                       b2, self.eps, 1.0 / self.world, L.stream()))
+            return 3
+        # barrier A: every rank's gradients are complete
+        dist.all_reduce(self._bar, group=self.pg)
+        L.check(lib.hrf_dp_reduce_adam(C.byref(self.peers), self.adam_desc.data_ptr(), len(self.params), 0, self.adam_blocks, 1, lr,
+                                       b1, b2, self.eps, 1.0 / self.world, L.stream()))
         # barrier B: every peer has read this rank's bucket and written this rank's shadow slices
-        dist.all_reduce(self._bar[:1], group=self.pg)
+        dist.all_reduce(self._bar, group=self.pg)
         self.grad.zero_()
-        return 7
+        return 6
+
+    def _scatter_and_exchange_overlapped(self, nat, samples, egrid, src, egrid_stride, ws, mark) -> int:
+        """exchange="p2p", overlapped: the scatter runs one hash grid per launch; as soon as grid k's launch is queued, a side
+        stream waits for it, passes a cross-rank barrier (all ranks' gradients of grid k complete) and runs the
+        reduce-scatter / Adam / shadow all-gather kernel over grid k's tensors -- while the main stream scatters grid k+1.
+        The small tensors follow the last grid; one closing barrier (all shadows written, all buckets read), the bucket is
+        cleared, and the main stream waits for the side stream."""
+        lib = L.lib()
+        lr = self.current_lr()
+        self.t += 1
+        b1, b2 = self.betas
+        main, side = torch.cuda.current_stream(), self._side
+        for k in range(4):
+            L.check(lib.hrf_field_backward_tables(C.byref(nat.field), C.byref(samples), self.sg_dev.data_ptr(), egrid, L.ptr(src),
+                                                  egrid_stride, ws.data_ptr(), k, 1, L.stream()))
+            ev = torch.cuda.Event()
+            ev.record(main)
+            with torch.cuda.stream(side):
+                side.wait_event(ev)
+                dist.all_reduce(self._bar, group=self.pg)
+                first, count = self.region_blocks[k]
+                L.check(lib.hrf_dp_reduce_adam(C.byref(self.peers), self.adam_desc.data_ptr(), len(self.params), first, count,
+                                               1 if k == 0 else 0, lr, b1, b2, self.eps, 1.0 / self.world, side.cuda_stream))
+        mark("scatter")
+        with torch.cuda.stream(side):
+            first, count = self.region_blocks[4]      # vectors (complete after the last scatter launch), MLPs, embeddings
+            L.check(lib.hrf_dp_reduce_adam(C.byref(self.peers), self.adam_desc.data_ptr(), len(self.params), first, count, 0, lr, b1,
+                                           b2, self.eps, 1.0 / self.world, side.cuda_stream))
+            dist.all_reduce(self._bar, group=self.pg)
+            self.grad.zero_()
+            done = torch.cuda.Event()
+            done.record(side)
+        main.wait_event(done)
+        mark("exchange+adam")
+        return 8 + 4 + 5 * 2 + 2
 
     def close(self) -> None:
         """Releases the peer-visible buffers (exchange="p2p").  Collective-free; call after the last step."""

@@ -347,8 +347,13 @@ typedef struct {
   int32_t vec_res;
   float* vectors_t;                  /* as hrf_adam_tensor */
 } hrf_dp_tensor;
+/* block_first / block_count: the range of blocks (in the first_block numbering of the descriptor table) this launch
+ * covers -- the whole table, or the tensors of one hash grid so that its exchange runs while the next grid's gradient is
+ * still being scattered.  advance_steps != 0 on the first launch of a step (it advances the step counters of the active
+ * tensors, once). */
 int hrf_dp_reduce_adam(const hrf_dp_peers* peers /* host */, const hrf_dp_tensor* tensors /* device */, int num_tensors,
-                       int64_t total_blocks, float lr, float beta1, float beta2, float eps, float grad_scale, void* stream);
+                       int64_t block_first, int64_t block_count, int advance_steps, float lr, float beta1, float beta2,
+                       float eps, float grad_scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Pre-processing that feeds the hot path.

@@ -52,7 +52,8 @@ def _train(rank, world, port, spans, q, exchange="p2p", segs=(6,), frame_plan=No
     b = synthetic_rays(512, 48, frames, seed=4, ragged=True)
     bg_all = torch.rand(512, 3, generator=torch.Generator().manual_seed(9))
     lo, hi = spans[rank]
-    tr = FusedTrainer(model, lr=1e-2, prune=False, world_size=world, exchange=exchange)
+    tr = FusedTrainer(model, lr=1e-2, prune=False, world_size=world, exchange=exchange.split("-")[0],
+                      overlap_exchange=not exchange.endswith("-serial"))
     for step in range(STEPS):
         if frame_plan is not None:
             pool = torch.tensor(frame_plan[step], dtype=torch.int32)
@@ -112,14 +113,18 @@ def _run_dp_case(cuda, exchange, segs, frame_plan, port_offset):
     _compare_with_single_process(got, ref, init)
 
 
-@pytest.mark.parametrize("exchange", ["nccl", "p2p"])
+EXCHANGES = ["nccl", "p2p", "p2p-serial"]
+
+
+@pytest.mark.parametrize("exchange", EXCHANGES)
 def test_two_rank_dp_equals_single_process(cuda, exchange):
-    """exchange="nccl": one all-reduce of the whole bucket, Adam on every rank; "p2p" (FusedTrainer's default): ONE kernel
-    doing reduce-scatter + rank-sharded Adam + all-gather of the bf16 shadows over NVLink peer memory."""
-    _run_dp_case(cuda, exchange, (6,), None, 1 if exchange == "p2p" else 0)
+    """exchange="nccl": one all-reduce of the whole bucket, Adam on every rank; "p2p" (FusedTrainer's default): the
+    reduce-scatter + rank-sharded Adam + all-gather of the bf16 shadows as a kernel over NVLink peer memory, one launch
+    per hash grid on a side stream while the next grid is scattered; "p2p-serial": the same kernel once, after the scatter."""
+    _run_dp_case(cuda, exchange, (6,), None, EXCHANGES.index(exchange))
 
 
-@pytest.mark.parametrize("exchange", ["nccl", "p2p"])
+@pytest.mark.parametrize("exchange", EXCHANGES)
 def test_two_rank_dp_multi_segment(cuda, exchange):
     """Three temporal segments; steps whose batches touch only some of them: a segment takes part in the step (gradient
     exchange, Adam, step counter) iff ANY rank's batch touches it -- the union-batch semantics of the reference's
@@ -127,7 +132,7 @@ def test_two_rank_dp_multi_segment(cuda, exchange):
     frames = list(range(15, 15 + 18))
     plan = [frames[0:3] + frames[12:15], frames[6:9], frames[0:18:3]]       # segments {0,2}, {1}, {0,1,2}
     assert STEPS == len(plan)
-    _run_dp_case(cuda, exchange, (6, 6, 6), plan, 3 if exchange == "p2p" else 2)
+    _run_dp_case(cuda, exchange, (6, 6, 6), plan, 3 + EXCHANGES.index(exchange))
 
 
 def test_tile_sharded_render_equals_monolithic(cuda):
