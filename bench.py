@@ -513,7 +513,7 @@ def main():
                     "L1/TEX gather pipe, see l1tex_pct / issue_slots_pct")
         else:
             # dominant kernel of the train step: the table-gradient scatter over the pruned samples
-            alg_per_sample, roof_kernel = ALG_BYTES_SCATTER, "grid_scatter_v2_kernel"
+            alg_per_sample, roof_kernel = ALG_BYTES_SCATTER, "grid_scatter_v3_kernel"
             kern_ms = phases.get("scatter", 0.0)
             achieved = alg_per_sample * kept_mean / max(kern_ms * 1e-3, 1e-9) / 1e9
             prof = committed_ncu("grid_scatter")
