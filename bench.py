@@ -352,7 +352,7 @@ def main():
         trainer = FusedTrainer(model, lr=float(os.environ.get("HRF_BENCH_LR", "1e-6")), world_size=world,
                                reuse=os.environ.get("HRF_TRAIN_REUSE", "feat+grid"),
                                exchange=os.environ.get("HRF_TRAIN_EXCHANGE", "p2p"),
-                               overlap_exchange=os.environ.get("HRF_DP_OVERLAP", "1") != "0")
+                               overlap_exchange=os.environ.get("HRF_DP_OVERLAP", "0") == "1")
         trainer.profile = True
     g = {k: v.to(dev).contiguous() for k, v in b.items() if k in ("o", "d", "frames", "t", "ri", "rgba")}
     n = g["t"].shape[0]

@@ -56,7 +56,7 @@ class FusedTrainer:
     def __init__(self, model: HumanRF, lr: float = 1e-2, betas=(0.9, 0.99), eps: float = 1e-15, lr_decay: float = 0.5,
                  max_steps: int = 50001, bce_loss_weight: float = 1e-3, huber_delta: float = 0.01,
                  render_step_size: float = 4e-4, world_size: int = 1, process_group=None, prune: bool = True,
-                 seed: int = 123, reuse: str = "feat", exchange: str = "p2p", overlap_exchange: bool = True):
+                 seed: int = 123, reuse: str = "feat", exchange: str = "p2p", overlap_exchange: bool = False):
         if reuse not in ("none", "feat", "feat+grid"):
             raise ValueError("reuse must be 'none', 'feat' or 'feat+grid'")
         if exchange not in ("p2p", "nccl"):
@@ -66,8 +66,9 @@ class FusedTrainer:
         self.bce_w, self.delta, self.step_size = bce_loss_weight, huber_delta, render_step_size
         self.world, self.pg, self.prune, self.reuse = world_size, process_group, prune, reuse
         self.exchange = exchange if world_size > 1 else "local"
-        # exchange="p2p": run the exchange of hash grid k (barrier + reduce/Adam/shadow kernel on a side stream) while grid
-        # k+1 is still being scattered; only the last grid's share, the small tensors and the closing barrier stay exposed
+        # exchange="p2p", optional: run the exchange of hash grid k (barrier + reduce/Adam/shadow kernel on a side stream)
+        # while grid k+1 is still being scattered.  Measured on 2 B200s (profiles/r2_dp_2gpu_overlap_ab.txt): the exposed
+        # exchange shrinks 0.46 -> 0.39 ms but four per-grid scatter launches cost 0.15 ms more than one: off by default.
         self.overlap_exchange = bool(overlap_exchange) and self.exchange == "p2p"
         self.rank = dist.get_rank(process_group) if world_size > 1 else 0
         self.params: List[torch.nn.Parameter] = model.hot_parameters()

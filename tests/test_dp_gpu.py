@@ -53,7 +53,7 @@ def _train(rank, world, port, spans, q, exchange="p2p", segs=(6,), frame_plan=No
     bg_all = torch.rand(512, 3, generator=torch.Generator().manual_seed(9))
     lo, hi = spans[rank]
     tr = FusedTrainer(model, lr=1e-2, prune=False, world_size=world, exchange=exchange.split("-")[0],
-                      overlap_exchange=not exchange.endswith("-serial"))
+                      overlap_exchange=exchange.endswith("-overlap"))
     for step in range(STEPS):
         if frame_plan is not None:
             pool = torch.tensor(frame_plan[step], dtype=torch.int32)
@@ -113,14 +113,14 @@ def _run_dp_case(cuda, exchange, segs, frame_plan, port_offset):
     _compare_with_single_process(got, ref, init)
 
 
-EXCHANGES = ["nccl", "p2p", "p2p-serial"]
+EXCHANGES = ["nccl", "p2p", "p2p-overlap"]
 
 
 @pytest.mark.parametrize("exchange", EXCHANGES)
 def test_two_rank_dp_equals_single_process(cuda, exchange):
     """exchange="nccl": one all-reduce of the whole bucket, Adam on every rank; "p2p" (FusedTrainer's default): the
-    reduce-scatter + rank-sharded Adam + all-gather of the bf16 shadows as a kernel over NVLink peer memory, one launch
-    per hash grid on a side stream while the next grid is scattered; "p2p-serial": the same kernel once, after the scatter."""
+    reduce-scatter + rank-sharded Adam + all-gather of the bf16 shadows as ONE kernel over NVLink peer memory after the
+    scatter; "p2p-overlap": the same kernel once per hash grid on a side stream while the next grid is scattered."""
     _run_dp_case(cuda, exchange, (6,), None, EXCHANGES.index(exchange))
 
 
