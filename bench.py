@@ -330,7 +330,7 @@ def main():
     L.lib()
     if args.mode in ("image", "sweep"):
         return run_image(args, dev, rank, world)
-    model, frames, b = build_workload(dev, seed=123 + rank)
+    model, frames, b = build_workload(dev, seed=int(os.environ.get("HRF_BENCH_SEED", "123")) + rank)
     trainer = None
     if args.mode == "train":
         from humanrf_b200.dataset.input_batch import InputBatch as _IB
@@ -415,6 +415,10 @@ def main():
         phases = {k: float(v) for k, v in zip(sorted(phases), ph.tolist())}
         trainer.profile = False
         kept_mean = sum(int(k) for k in kept) / max(len(kept), 1)
+        kept_ranks = torch.tensor([kept_mean, -kept_mean], device=dev, dtype=torch.float64)
+        if world > 1:   # every rank draws its own ray batch: report the spread of the per-rank work
+            dist.all_reduce(kept_ranks, op=dist.ReduceOp.MAX)
+        kept_max, kept_min = float(kept_ranks[0].item()), -float(kept_ranks[1].item())
 
     # ---- e2e through the public API with pinned host buffers -------------------------------------
     host = {k: b[k].contiguous().pin_memory() for k in ("o", "d", "frames", "t", "ri", "rgba")}
@@ -543,7 +547,8 @@ def main():
         }
         if args.mode == "train":
             line["e2e"]["samples_after_prune_mean"] = sum(int(k) for k in e2e_kept[-k_e2e:]) / k_e2e
-            line["config"].update({"samples_after_prune_mean": kept_mean, "reuse": trainer.reuse, "exchange": trainer.exchange,
+            line["config"].update({"samples_after_prune_mean": kept_mean, "samples_after_prune_rank_min_max": [kept_min, kept_max],
+                                   "reuse": trainer.reuse, "exchange": trainer.exchange,
                                    "lr": trainer.lr,
                                    "note": "prune pass over all 2,097,152 candidates, fwd+bwd+Adam over the survivors; targets are the "
                                            "initial model's own rendering so the workload is stationary"})
