@@ -746,6 +746,9 @@ int hrf_launch_scatter_v3(const hrf_field* f, const hrf_samples* s, const hrf_se
 int hrf_launch_scatter_v4(const hrf_field* f, const hrf_samples* s, const hrf_segment_grads* seg_grads, const void* grid_feat_bf16,
                           const int32_t* feat_index, int64_t grid_feat_stride, const void* workspace, int grid_first, int grid_count,
                           cudaStream_t st);   // scatter_v4.cu
+int hrf_launch_scatter_v5(const hrf_field* f, const hrf_samples* s, const hrf_segment_grads* seg_grads, const void* grid_feat_bf16,
+                          const int32_t* feat_index, int64_t grid_feat_stride, const void* workspace, int grid_first, int grid_count,
+                          cudaStream_t st);   // scatter_v5.cu
 #ifndef HRF_SCATTER_DEFAULT
 #define HRF_SCATTER_DEFAULT 3   // measured on B200 (profiles/r2d_*): v3 1.50 ms, v1 1.71, v2 1.86
 #endif
@@ -757,9 +760,12 @@ extern "C" int hrf_field_backward_tables(const hrf_field* f, const hrf_samples* 
   HRF_REQUIRE(grid_first >= 0 && grid_count >= 1 && grid_first + grid_count <= 4, "grids are 0..3 (xyz, xyt, yzt, xzt)");
   if (s->num_samples == 0) return 0;
   HRF_REQUIRE(workspace != nullptr, "needs the workspace hrf_field_backward_mlp filled");
-  // HRF_SCATTER = 4 | 3 | 2 | 1 (read per call: the tests switch it): scatter_v4.cu, scatter_v3.cu, scatter_v2.cu, the
+  // HRF_SCATTER = 5 | 4 | 3 | 2 | 1 (read per call: the tests switch it): scatter_v5.cu ... scatter_v2.cu, the
   // first-generation kernels below.  All stay built: each is the others' cross-check in tests/test_scatter_gpu.py.
-  const int gen = [] { const char* e = getenv("HRF_SCATTER"); const int v = e ? atoi(e) : HRF_SCATTER_DEFAULT; return (v >= 1 && v <= 4) ? v : HRF_SCATTER_DEFAULT; }();
+  const int gen = [] { const char* e = getenv("HRF_SCATTER"); const int v = e ? atoi(e) : HRF_SCATTER_DEFAULT; return (v >= 1 && v <= 5) ? v : HRF_SCATTER_DEFAULT; }();
+  if (gen == 5)
+    return hrf_launch_scatter_v5(f, s, seg_grads, grid_feat_bf16, feat_index, grid_feat_stride, workspace, grid_first, grid_count,
+                                 reinterpret_cast<cudaStream_t>(stream));
   if (gen == 4)
     return hrf_launch_scatter_v4(f, s, seg_grads, grid_feat_bf16, feat_index, grid_feat_stride, workspace, grid_first, grid_count,
                                  reinterpret_cast<cudaStream_t>(stream));

@@ -23,18 +23,19 @@ def _relnorm(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
-@pytest.mark.parametrize("staged,carry,chunk,taps", [("v4", "5", "", ""), ("v3", "6", "", ""), ("v3", "5", "", ""), ("v2", "6", "", ""), ("v2", "5", "", ""),
+@pytest.mark.parametrize("staged,carry,chunk,taps", [("v5", "5", "", ""), ("v4", "5", "", ""), ("v3", "6", "", ""), ("v3", "5", "", ""), ("v2", "6", "", ""), ("v2", "5", "", ""),
                                                      ("1", "1", "8", "0"), ("1", "1", "8", "1"), ("1", "0", "8", "1"), ("0", "1", "16", "0"),
                                                      ("0", "0", "8", "0"), ("0", "1", "5", "0")],
-                         ids=["v4-split-slots", "v3-warp-private", "v3-5ctas", "v2-parity-slots", "v2-5ctas", "staged", "staged-tapstage",
+                         ids=["v5-lane-pairs", "v4-split-slots", "v3-warp-private", "v3-5ctas", "v2-parity-slots", "v2-5ctas", "staged", "staged-tapstage",
                               "staged-tapstage-nocarry", "strided16", "strided8-nocarry", "strided5"])
 def test_table_scatter_matches_float64_autograd(cuda, monkeypatch, staged, carry, chunk, taps):
-    """Every generation of the scatter (HRF_SCATTER = 4 | 3 | 2 | 1): v4 = csrc/scatter_v4.cu (the 8 parity slots of a sample
+    """Every generation of the scatter (HRF_SCATTER = 5 | 4 | 3 | 2 | 1): v5 = csrc/scatter_v5.cu (the parity slots split over a
+    lane pair by the parity of the first-axis vertex, pair-wide flushes), v4 = csrc/scatter_v4.cu (the 8 parity slots of a sample
     chunk split over two threads), v3 = csrc/scatter_v3.cu (parity-slot accumulators,
     warp-private staging, transposed vector rows), v2 = csrc/scatter_v2.cu (parity slots, block staging), staged / strided
     = the first-generation kernels (shared-memory staging with the shifted-corner carry; the strided first kernel behind
     HRF_SCATTER_STAGED=0)."""
-    if staged in ("v2", "v3", "v4"):
+    if staged in ("v2", "v3", "v4", "v5"):
         monkeypatch.setenv("HRF_SCATTER", staged[1])
         monkeypatch.setenv("HRF_SCATTER_CTAS", carry)
         staged, carry, chunk, taps = "1", "1", "8", "0"
