@@ -297,7 +297,29 @@ __device__ __forceinline__ void scatter_levels5(const ScatterV5Args& a, V5Smem& 
     if (gtab != nullptr) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) red2v5(gtab + 2 * (size_t)idx[q], accx[q], accy[q]);
-      red2v5(gvec + to * HRF_N_FEATURES, va0, va1);
+      if (kAxis != 3) red2v5(gvec + to * HRF_N_FEATURES, va0, va1);
+    }
+    if (kAxis == 3) {
+      // The vector axis of grid xyz is TIME: every sample of a ray has the same two rows, and a batch holds a handful of
+      // frames (max_num_frames_per_batch, run_args.py:101), so the whole launch adds into ~16 rows x 16 levels = a few
+      // 128-byte lines.  Same-line REDs serialise in one L2 slice (ncu: busiest slice 69 % against 44 % on average, and the
+      // kernel time moved 15 % with the choice of frames at identical sample counts, profiles/r2j_seed_spread.txt).  The
+      // lanes of a warp walk ~1 ray: sum the lanes that hold the same row first, one RED per distinct row and warp.
+      const uint32_t key = gtab != nullptr ? ((cur_sgi << 24) | to) : 0xffffffffu;    // (vec_res < 2^24)
+      uint32_t rem = __ballot_sync(0xffffffffu, key != 0xffffffffu);
+      while (rem != 0u) {                                // (warp-uniform)
+        const int leader = __ffs(rem) - 1;
+        const uint32_t k = __shfl_sync(0xffffffffu, key, leader);
+        const bool mine = key == k;
+        float s0 = mine ? va0 : 0.f, s1 = mine ? va1 : 0.f;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+          s0 += __shfl_xor_sync(0xffffffffu, s0, d);
+          s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+        }
+        if (lane == leader) red2v5(gvec + to * HRF_N_FEATURES, s0, s1);
+        rem &= ~__ballot_sync(0xffffffffu, mine);
+      }
     }
     if (p == 0u && slow_mask != 0u) {   // cold: samples outside a dense level's grid, all 8 corners, even lane only
       for (int j = 0; j < kV5Chunk; ++j) {
