@@ -389,4 +389,28 @@ __device__ __forceinline__ void issue_layer(uint32_t tmem_d, uint32_t a_addr, ui
   }
 }
 
+// Gradient of the TIME rows of `vectors` (grid xyz, tensor_composition.cu:49-52,109-111).  Every sample of a ray has the
+// same two rows and a batch holds a handful of frames (max_num_frames_per_batch, run_args.py:101): a whole scatter launch
+// adds into ~16 rows x 16 levels, i.e. a few 128-byte lines, and same-line REDs serialise in one L2 slice (measured: the
+// busiest slice at 69 % against 44 % on average; 1.42 -> 1.07 ms once these adds were combined, profiles/r2j_*, r2k_*).
+// The lanes of a warp walk about one ray: sum the lanes that hold the same row, one RED per distinct row and warp.
+// `key` identifies the row (0xffffffff: nothing to add), `addr` is the same for equal keys.  All 32 lanes must call.
+__device__ __forceinline__ void warp_combine_red2(uint32_t key, float* addr, float s0, float s1) {
+  const int lane = threadIdx.x & 31;
+  uint32_t rem = __ballot_sync(0xffffffffu, key != 0xffffffffu);
+  while (rem != 0u) {                                // (warp-uniform)
+    const int leader = __ffs(rem) - 1;
+    const uint32_t k = __shfl_sync(0xffffffffu, key, leader);
+    const bool mine = key == k;
+    float t0 = mine ? s0 : 0.f, t1 = mine ? s1 : 0.f;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      t0 += __shfl_xor_sync(0xffffffffu, t0, d);
+      t1 += __shfl_xor_sync(0xffffffffu, t1, d);
+    }
+    if (lane == leader) asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(t0), "f"(t1));
+    rem &= ~__ballot_sync(0xffffffffu, mine);
+  }
+}
+
 }  // namespace hrf

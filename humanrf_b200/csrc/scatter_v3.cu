@@ -306,8 +306,14 @@ __device__ __forceinline__ void scatter_levels(const ScatterV3Args& a, V3Smem& s
     if (gtab != nullptr) {
 #pragma unroll
       for (int q = 0; q < 8; ++q) red2(gtab + 2 * (size_t)idx[q], accx[q], accy[q]);
-      red2(gvec + to0 * HRF_N_FEATURES, va0, va1);
-      red2(gvec + to1 * HRF_N_FEATURES, vb0, vb1);
+      if (kAxis != 3) {
+        red2(gvec + to0 * HRF_N_FEATURES, va0, va1);
+        red2(gvec + to1 * HRF_N_FEATURES, vb0, vb1);
+      }
+    }
+    if (kAxis == 3) {   // grid xyz: the vector axis is time, a few hot rows: summed across the warp first (field_common.cuh)
+      warp_combine_red2(gtab != nullptr ? ((cur_sgi << 24) | to0) : 0xffffffffu, gvec + to0 * HRF_N_FEATURES, va0, va1);
+      warp_combine_red2(gtab != nullptr ? ((cur_sgi << 24) | to1) : 0xffffffffu, gvec + to1 * HRF_N_FEATURES, vb0, vb1);
     }
     if (slow_mask != 0u) {   // cold: samples outside a dense level's grid, one by one with the forward's general index wrap
       for (int j = 0; j < cnt; ++j) {
@@ -362,6 +368,7 @@ using namespace hrf;
 int hrf_launch_scatter_v3(const hrf_field* f, const hrf_samples* s, const hrf_segment_grads* seg_grads, const void* grid_feat_bf16,
                           const int32_t* feat_index, int64_t grid_feat_stride, const void* workspace, int grid_first, int grid_count,
                           cudaStream_t st) {
+  HRF_REQUIRE(f->vec_res < (1 << 24), "the scatter keys vector rows in 24 bits");
   ScatterV3Args a;
   a.f = *f;
   a.s = *s;

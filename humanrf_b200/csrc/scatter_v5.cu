@@ -299,28 +299,8 @@ __device__ __forceinline__ void scatter_levels5(const ScatterV5Args& a, V5Smem& 
       for (int q = 0; q < 4; ++q) red2v5(gtab + 2 * (size_t)idx[q], accx[q], accy[q]);
       if (kAxis != 3) red2v5(gvec + to * HRF_N_FEATURES, va0, va1);
     }
-    if (kAxis == 3) {
-      // The vector axis of grid xyz is TIME: every sample of a ray has the same two rows, and a batch holds a handful of
-      // frames (max_num_frames_per_batch, run_args.py:101), so the whole launch adds into ~16 rows x 16 levels = a few
-      // 128-byte lines.  Same-line REDs serialise in one L2 slice (ncu: busiest slice 69 % against 44 % on average, and the
-      // kernel time moved 15 % with the choice of frames at identical sample counts, profiles/r2j_seed_spread.txt).  The
-      // lanes of a warp walk ~1 ray: sum the lanes that hold the same row first, one RED per distinct row and warp.
-      const uint32_t key = gtab != nullptr ? ((cur_sgi << 24) | to) : 0xffffffffu;    // (vec_res < 2^24)
-      uint32_t rem = __ballot_sync(0xffffffffu, key != 0xffffffffu);
-      while (rem != 0u) {                                // (warp-uniform)
-        const int leader = __ffs(rem) - 1;
-        const uint32_t k = __shfl_sync(0xffffffffu, key, leader);
-        const bool mine = key == k;
-        float s0 = mine ? va0 : 0.f, s1 = mine ? va1 : 0.f;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-          s0 += __shfl_xor_sync(0xffffffffu, s0, d);
-          s1 += __shfl_xor_sync(0xffffffffu, s1, d);
-        }
-        if (lane == leader) red2v5(gvec + to * HRF_N_FEATURES, s0, s1);
-        rem &= ~__ballot_sync(0xffffffffu, mine);
-      }
-    }
+    if (kAxis == 3)   // grid xyz: the vector axis is time, a few hot rows: summed across the warp first (field_common.cuh)
+      warp_combine_red2(gtab != nullptr ? ((cur_sgi << 24) | to) : 0xffffffffu, gvec + to * HRF_N_FEATURES, va0, va1);
     if (p == 0u && slow_mask != 0u) {   // cold: samples outside a dense level's grid, all 8 corners, even lane only
       for (int j = 0; j < kV5Chunk; ++j) {
         if (!((slow_mask >> j) & 1u)) continue;
@@ -373,6 +353,7 @@ using namespace hrf;
 int hrf_launch_scatter_v5(const hrf_field* f, const hrf_samples* s, const hrf_segment_grads* seg_grads, const void* grid_feat_bf16,
                           const int32_t* feat_index, int64_t grid_feat_stride, const void* workspace, int grid_first, int grid_count,
                           cudaStream_t st) {
+  HRF_REQUIRE(f->vec_res < (1 << 24), "scatter v5 keys vector rows in 24 bits");
   ScatterV5Args a;
   a.f = *f;
   a.s = *s;

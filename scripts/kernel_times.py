@@ -96,6 +96,12 @@ def main():
 
     timeit("backward MLP kernel (saved feat)", bwd_mlp)
 
+    def bwd_mlp_noflush():   # d_mlp NULL: the weight-gradient accumulators are computed but not added to global memory
+        L.check(lib.hrf_field_backward_mlp(C.byref(nat.field), C.byref(s), d_sigma.data_ptr(), d_rgb.data_ptr(), None, feat.data_ptr(),
+                                           None, None, None, ws.data_ptr(), L.stream()))
+
+    timeit("backward MLP kernel, no weight-gradient flush", bwd_mlp_noflush)
+
     def scatter(eg):
         L.check(lib.hrf_field_backward_tables(C.byref(nat.field), C.byref(s), sg_dev.data_ptr(), eg, None, 0, ws.data_ptr(), 0, 4, L.stream()))
 
