@@ -19,6 +19,8 @@ for m in ('train','render'):
 done
 python scripts/kernel_times.py --segments 100 100 50 --reps 5 > gpurun_out/${R}_kernel_times_seg100-100-50.txt 2>&1
 python scripts/kernel_times.py --segments 50 > gpurun_out/${R}_kernel_times_seg50.txt 2>&1
+HRF_SCATTER_CTAS=6 HRF_BWD_UNROLL=1 python scripts/kernel_times.py --segments 50 2>&1 | grep -i "scatter\|backward MLP" | sed "s/^/v3-6ctas, bwd unroll 1: /" > gpurun_out/${R}_kernel_times_variants.txt
+python scripts/seed_spread.py > gpurun_out/${R}_seed_spread.txt 2>&1
 python scripts/image_phases.py > gpurun_out/${R}_image_phases.txt 2>&1; tail -1 gpurun_out/${R}_image_phases.txt
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${R}_launches_train.csv \
     python bench.py --mode train --steps 2 --warmup 3 --no-cpu-baseline --no-companions > gpurun_out/ncu_l_train.log 2>&1
