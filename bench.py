@@ -522,12 +522,16 @@ def main():
                     "L1/TEX gather pipe, see l1tex_pct / issue_slots_pct")
         else:
             # dominant kernel of the train step: the table-gradient scatter over the pruned samples
-            alg_per_sample, roof_kernel = ALG_BYTES_SCATTER, "grid_scatter_v3_kernel"
+            gen = os.environ.get("HRF_SCATTER", "3")      # the library's default generation (csrc/field_bwd.cu HRF_SCATTER_DEFAULT)
+            gen = gen if gen in ("2", "3", "4", "5") else "3"
+            alg_per_sample, roof_kernel = ALG_BYTES_SCATTER, f"grid_scatter_v{gen}_kernel"
             kern_ms = phases.get("scatter", 0.0)
             achieved = alg_per_sample * kept_mean / max(kern_ms * 1e-3, 1e-9) / 1e9
-            prof = committed_ncu("grid_scatter")
+            prof = committed_ncu(roof_kernel)
             note = ("SURVEY 8d backward convention: 2 x 2048 B table-gradient RMW + 2 x 1024 B vector-gradient RMW per surviving "
-                    "sample; the RMWs are L2 atomics (red.global.add.v2.f32), the physical limiter is issue slots / L2 RED rate")
+                    "sample; the RMWs are L2 atomics (red.global.add.v2.f32) that run-length and warp-level combining keep off "
+                    "DRAM, so the convention's bytes are not physical traffic (see traffic); physical limiters: L1TEX RED "
+                    "wavefronts, L2 RED requests, issue slots (l1tex_pct / l2_pct / issue_slots_pct)")
         line = {
             "metric": METRIC[args.mode], "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
