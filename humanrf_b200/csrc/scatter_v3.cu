@@ -166,7 +166,7 @@ __device__ __forceinline__ void scatter_levels(const ScatterV3Args& a, V3Smem& s
     float* gvec = nullptr;
     const uint32_t* tab = nullptr;
     const float* vecs = nullptr;
-    uint32_t lsize = 1u, mulY = 0u, mulZ = 0u, hmask = 0u, vstride = 2u;
+    uint32_t lsize = 1u, mulY = 0u, mulZ = 0u, hmask = 0u, vstride = 2u, gstride = (uint32_t)HRF_N_FEATURES;
     bool hashed = false;
     uint32_t to0 = 0u, to1 = 0u;          // current tap rows of the vector axis (valid once gtab != nullptr)
     float va0 = 0.f, va1 = 0.f, vb0 = 0.f, vb1 = 0.f;
@@ -200,8 +200,8 @@ __device__ __forceinline__ void scatter_levels(const ScatterV3Args& a, V3Smem& s
             red2(gtab + 2 * (size_t)idx[q], accx[q], accy[q]);
             accx[q] = accy[q] = 0.f;
           }
-          red2(gvec + to0 * HRF_N_FEATURES, va0, va1);
-          red2(gvec + to1 * HRF_N_FEATURES, vb0, vb1);
+          red2(gvec + to0 * gstride, va0, va1);
+          red2(gvec + to1 * gstride, vb0, vb1);
           va0 = va1 = vb0 = vb1 = 0.f;
         }
         const hrf_segment* sg = f.segments + sgi;
@@ -217,7 +217,12 @@ __device__ __forceinline__ void scatter_levels(const ScatterV3Args& a, V3Smem& s
         vstride = sg->vectors_t != nullptr ? 2u : (uint32_t)HRF_N_FEATURES;
         vecs = sg->vectors_t != nullptr ? sg->vectors_t + (size_t)(kAxis * HRF_N_LEVELS + l) * f.vec_res * 2
                                         : sg->vectors + (size_t)kAxis * f.vec_res * HRF_N_FEATURES + 2 * l;
-        gvec = a.seg_grads[sgi].vectors + (size_t)kAxis * f.vec_res * HRF_N_FEATURES + 2 * l;
+        // the vector-row gradient: into the transposed scratch when the caller gave one (row stride 2 floats: the two tap
+        // rows and the neighbouring samples' rows share lines), else into `vectors` itself (row stride 32)
+        gstride = a.seg_grads[sgi].vectors_t != nullptr ? 2u : (uint32_t)HRF_N_FEATURES;
+        gvec = a.seg_grads[sgi].vectors_t != nullptr
+                   ? a.seg_grads[sgi].vectors_t + (size_t)(kAxis * HRF_N_LEVELS + l) * f.vec_res * 2
+                   : a.seg_grads[sgi].vectors + (size_t)kAxis * f.vec_res * HRF_N_FEATURES + 2 * l;
         gtab = a.seg_grads[sgi].grid[kGrid] + 2 * (size_t)off;
         // start the runs AT this sample: its own vertices / taps are the current ones, so the step below finds nothing to
         // flush (the accumulators are zero) and the hot path needs no "slot is empty" test
@@ -244,8 +249,8 @@ __device__ __forceinline__ void scatter_levels(const ScatterV3Args& a, V3Smem& s
       // ---- vector tap of this sample (tensor_composition.cu:37-45); a new tap pair flushes the gradient run.  The two
       // rows are fetched every step (L1 hits, issued here, consumed after the index work below): no stall on them.
       if (tp.i0 != to0 || tp.i1 != to1) {
-        red2(gvec + to0 * HRF_N_FEATURES, va0, va1);
-        red2(gvec + to1 * HRF_N_FEATURES, vb0, vb1);
+        red2(gvec + to0 * gstride, va0, va1);
+        red2(gvec + to1 * gstride, vb0, vb1);
         va0 = va1 = vb0 = vb1 = 0.f;
         to0 = tp.i0, to1 = tp.i1;
       }
@@ -307,13 +312,13 @@ __device__ __forceinline__ void scatter_levels(const ScatterV3Args& a, V3Smem& s
 #pragma unroll
       for (int q = 0; q < 8; ++q) red2(gtab + 2 * (size_t)idx[q], accx[q], accy[q]);
       if (kAxis != 3) {
-        red2(gvec + to0 * HRF_N_FEATURES, va0, va1);
-        red2(gvec + to1 * HRF_N_FEATURES, vb0, vb1);
+        red2(gvec + to0 * gstride, va0, va1);
+        red2(gvec + to1 * gstride, vb0, vb1);
       }
     }
     if (kAxis == 3) {   // grid xyz: the vector axis is time, a few hot rows: summed across the warp first (field_common.cuh)
-      warp_combine_red2(gtab != nullptr ? ((cur_sgi << 24) | to0) : 0xffffffffu, gvec + to0 * HRF_N_FEATURES, va0, va1);
-      warp_combine_red2(gtab != nullptr ? ((cur_sgi << 24) | to1) : 0xffffffffu, gvec + to1 * HRF_N_FEATURES, vb0, vb1);
+      warp_combine_red2(gtab != nullptr ? ((cur_sgi << 24) | to0) : 0xffffffffu, gvec + to0 * gstride, va0, va1);
+      warp_combine_red2(gtab != nullptr ? ((cur_sgi << 24) | to1) : 0xffffffffu, gvec + to1 * gstride, vb0, vb1);
     }
     if (slow_mask != 0u) {   // cold: samples outside a dense level's grid, one by one with the forward's general index wrap
       for (int j = 0; j < cnt; ++j) {

@@ -23,10 +23,10 @@ def _relnorm(a, b):
     return float((a - b).norm() / b.norm().clamp_min(1e-30))
 
 
-@pytest.mark.parametrize("staged,carry,chunk,taps", [("v5", "5", "", ""), ("v4", "5", "", ""), ("v3", "6", "", ""), ("v3", "5", "", ""), ("v2", "6", "", ""), ("v2", "5", "", ""),
+@pytest.mark.parametrize("staged,carry,chunk,taps", [("v3", "5", "", "vt"), ("v5", "5", "", ""), ("v4", "5", "", ""), ("v3", "6", "", ""), ("v3", "5", "", ""), ("v2", "6", "", ""), ("v2", "5", "", ""),
                                                      ("1", "1", "8", "0"), ("1", "1", "8", "1"), ("1", "0", "8", "1"), ("0", "1", "16", "0"),
                                                      ("0", "0", "8", "0"), ("0", "1", "5", "0")],
-                         ids=["v5-lane-pairs", "v4-split-slots", "v3-warp-private", "v3-5ctas", "v2-parity-slots", "v2-5ctas", "staged", "staged-tapstage",
+                         ids=["v3-transposed-vector-grads", "v5-lane-pairs", "v4-split-slots", "v3-warp-private", "v3-5ctas", "v2-parity-slots", "v2-5ctas", "staged", "staged-tapstage",
                               "staged-tapstage-nocarry", "strided16", "strided8-nocarry", "strided5"])
 def test_table_scatter_matches_float64_autograd(cuda, monkeypatch, staged, carry, chunk, taps):
     """Every generation of the scatter (HRF_SCATTER = 5 | 4 | 3 | 2 | 1): v5 = csrc/scatter_v5.cu (the parity slots split over a
@@ -35,6 +35,7 @@ def test_table_scatter_matches_float64_autograd(cuda, monkeypatch, staged, carry
     warp-private staging, transposed vector rows), v2 = csrc/scatter_v2.cu (parity slots, block staging), staged / strided
     = the first-generation kernels (shared-memory staging with the shifted-corner carry; the strided first kernel behind
     HRF_SCATTER_STAGED=0)."""
+    vec_t = taps == "vt"     # v3 with the vector-row gradient accumulated in the transposed scratch + hrf_fold_vector_grads
     if staged in ("v2", "v3", "v4", "v5"):
         monkeypatch.setenv("HRF_SCATTER", staged[1])
         monkeypatch.setenv("HRF_SCATTER_CTAS", carry)
@@ -87,11 +88,18 @@ def test_table_scatter_matches_float64_autograd(cuda, monkeypatch, staged, carry
         for k in range(4):
             sg[s].grid[k] = grads[5 * s + k].data_ptr()
         sg[s].vectors = grads[5 * s + 4].data_ptr()
+    scratch = [torch.zeros_like(grads[5 * s + 4]).reshape(-1) for s in range(m.num_segments)] if vec_t else []
+    for s, t_ in enumerate(scratch):
+        sg[s].vectors_t = t_.data_ptr()
     sg_dev = torch.from_numpy(np.frombuffer(bytes(sg), dtype=np.uint8).copy()).to(cuda)
     samples = nat.samples_query(pos.to(cuda).contiguous(), None, fr.to(cuda).to(torch.int32).contiguous())
     for first, count in ((0, 1), (1, 3)):                      # split launches (per-table schedule)
         L.check(L.lib().hrf_field_backward_tables(C.byref(nat.field), C.byref(samples), sg_dev.data_ptr(), None, None, 0, ws.data_ptr(),
                                                   first, count, L.stream()))
+    for s, t_ in enumerate(scratch):
+        assert float(grads[5 * s + 4].abs().max()) == 0.0 and float(t_.abs().max()) > 0.0   # nothing went to `vectors` directly
+        L.check(L.lib().hrf_fold_vector_grads(t_.data_ptr(), grads[5 * s + 4].data_ptr(), grads[5 * s + 4].shape[1], L.stream()))
+        assert float(t_.abs().max()) == 0.0                                                   # scratch left zeroed
     torch.cuda.synchronize()
     for s in range(m.num_segments):
         for k in range(4):
