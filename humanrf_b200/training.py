@@ -100,11 +100,13 @@ class FusedTrainer:
             for k in range(4):
                 sg[s_].grid[k] = self.grad_views[5 * s_ + k].data_ptr()
             sg[s_].vectors = self.grad_views[5 * s_ + 4].data_ptr()
-        # The scatter accumulates the vector-row gradients in a transposed scratch ([4][16][VR][2]: the rows neighbouring
-        # samples touch share 128-byte lines, a third fewer L2 RED requests per launch); hrf_fold_vector_grads adds it into
-        # the bucket (and re-zeroes it) before Adam / the exchange read the gradient.  HRF_VECGRAD_T=0: straight into the bucket.
+        # HRF_VECGRAD_T=1 (experiment, off): the scatter accumulates the vector-row gradients in a transposed scratch
+        # ([4][16][VR][2]: the rows neighbouring samples touch share 128-byte lines) and hrf_fold_vector_grads adds it into
+        # the bucket before Adam / the exchange read the gradient.  Measured on B200 (profiles/r2n_*): L2 RED requests
+        # 141 M -> 118 M, L1TEX 73 -> 57 %, L2 62 -> 50 % -- and the kernel SLOWER, 1.02 -> 1.09 ms: packing the adds of
+        # neighbouring lanes into the same lines makes them queue behind each other in the L2's atomic units.
         self.vec_grad_t = None
-        if os.environ.get("HRF_VECGRAD_T", "1") != "0":
+        if os.environ.get("HRF_VECGRAD_T", "0") == "1":
             vn = self.grad_views[4].numel()
             self.vec_grad_t = torch.zeros(S * vn, dtype=torch.float32, device=dev)
             for s_ in range(S):

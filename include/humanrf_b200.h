@@ -233,8 +233,9 @@ typedef struct {
   /* Optional scratch in the transposed layout of hrf_segment.vectors_t, [4 axes][16 levels][vec_res][2], zeroed by the
    * caller once.  When non-NULL the default scatter generation accumulates the vector-row gradient THERE instead of in
    * `vectors`: the two tap rows of a sample, and the rows of the neighbouring samples of a ray, then share 128-byte lines
-   * (16 rows of one level per line instead of one row of 16 levels), which cuts the L2 RED requests of the launch by a
-   * third.  The caller folds it back with hrf_fold_vector_grads before anything reads `vectors`.  The other scatter
+   * (16 rows of one level per line instead of one row of 16 levels): 16 % fewer L2 RED requests per launch, but measured
+   * 6 % SLOWER on B200 (same-line adds queue in the L2 atomic units), so humanrf_b200.training leaves it NULL by default.
+   * The caller folds it back with hrf_fold_vector_grads before anything reads `vectors`.  The other scatter
    * generations ignore the field and add into `vectors` directly, so the fold is always correct. */
   float* vectors_t;
 } hrf_segment_grads;
