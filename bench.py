@@ -422,6 +422,11 @@ def main():
 
     # ---- e2e through the public API with pinned host buffers -------------------------------------
     host = {k: b[k].contiguous().pin_memory() for k in ("o", "d", "frames", "t", "ri", "rgba")}
+    # The ray index of a sample travels as int32 (FusedTrainer.step / volume_rendering.render widen it on the device): 8
+    # instead of 17 MB per step.  With int64 the 25 MB upload needs 10.8 GB/s to hide behind a 2.35 ms train step (24 GB/s
+    # behind a 1.03 ms render step), which not every host of this pool sustains from pinned memory: the train e2e moved
+    # 1.54-1.72 M rays/s from box to box (profiles/r2k-r2n).
+    host["ri"] = b["ri"].to(torch.int32).contiguous().pin_memory()
     host_color = torch.empty(RAYS, 3).pin_memory()
     h2d = sum(host[k].numel() * host[k].element_size() for k in ("o", "d", "frames", "t", "ri"))
     d2h = host_color.numel() * 4

@@ -256,7 +256,8 @@ class FusedTrainer:
 
     def step(self, o, d, frames, t, ri, rgba, num_rays: int, kernel_event=None, return_loss: bool = False,
              background: Optional[torch.Tensor] = None, cameras: Optional[torch.Tensor] = None, bwd_events=None):
-        """One optimisation step on a ray batch given in InputBatch layout (device tensors).  Nothing in here reads
+        """One optimisation step on a ray batch given in InputBatch layout (device tensors; `ri` int64 as in the reference's
+        InputBatch.ray_indices, or int32).  Nothing in here reads
         the device back: the step is enqueued and the call returns.  Returns the number of kernels launched, or the
         loss value when return_loss (that one read is the caller's choice)."""
         lib, nat, dev = L.lib(), self.model.native(), t.device
@@ -272,6 +273,8 @@ class FusedTrainer:
         mark("start")
         step = self.step_size
         t = t.reshape(-1)
+        if ri.dtype != torch.int64:      # int32 ray indices are accepted (a third of the bytes of a host upload) and widened here
+            ri = ri.long()
         S = self.model.num_segments
         cams = cameras if self.model.camera_embedding_dim > 0 else None
         # Segments this batch touches (humanrf.py:162-179): the reference gives the others no gradient, so Adam leaves

@@ -54,6 +54,22 @@ def test_prune_path_runs(cuda):
     assert 0 < tr.last["samples"] <= g["t"].shape[0]
 
 
+def test_int32_ray_indices_train_like_int64(cuda):
+    """FusedTrainer.step accepts the ray index of a sample as int32 (a third of the upload of a host batch) and widens it on
+    the device: the same seeds give the same losses as with the reference's int64 indices."""
+    from humanrf_b200.training import FusedTrainer
+
+    losses = []
+    for dt in (torch.int64, torch.int32):
+        model, frames = make_model((6,), table_std=0.5, device=cuda)
+        b = synthetic_rays(256, 128, frames, seed=5, ragged=True)
+        g = {k: v.to(cuda).contiguous() for k, v in b.items() if k in ("o", "d", "frames", "t", "ri", "rgba")}
+        tr = FusedTrainer(model, prune=True, seed=3)
+        losses.append([tr.step(g["o"], g["d"], g["frames"], g["t"], g["ri"].to(dt), g["rgba"], 256, return_loss=True) for _ in range(3)])
+    assert losses[0][0] == losses[1][0], losses                      # first step: forward only, deterministic
+    assert np.allclose(losses[0], losses[1], rtol=1e-4), losses      # later steps: fp32 atomics sum in any order
+
+
 def test_multi_segment_steps_follow_the_reference_optimizer(cuda):
     """Three temporal segments, batches that touch only some of them.  The reference runs only the touched segments
     (humanrf.py:162-179), zero_grad(set_to_none=True) leaves the others' .grad at None (trainer.py:174) and
