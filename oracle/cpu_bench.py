@@ -5,7 +5,7 @@
                  Adam update of all parameters (run.py:101-104) in the parent with every host thread
 The sample batch is split by rays over a fork()ed process pool (one single-threaded worker per core; the model is built
 once and shared copy-on-write).  The number of rays per worker is chosen from a calibration step so that the whole
-run fits `--budget-s` (never fewer than 16 rays per worker: below that, process-pool overhead dominates and the figure
+run fits `--budget-s` (never fewer than 16 rays per worker unless a 16-ray step takes seconds: below that, process-pool overhead dominates and the figure
 is not reproducible).  Prints one JSON line.  Run as a separate process by bench.py so that no CUDA context is forked."""
 from __future__ import annotations
 
@@ -107,9 +107,13 @@ def main():
 
     rpw = a.rays_per_worker
     if rpw <= 0:
-        _, sec = run(16, 1, 1)                                # calibration (page-in + one timed step at the minimum size)
+        _, sec = run(16, 1, 1)                                # calibration (page-in + one timed step at 16 rays per worker)
         per_step = a.budget_s / max(a.steps + a.warmup, 1)
-        rpw = int(min(64, max(16, 16 * per_step / max(sec, 1e-3))))
+        # Floor: 16 rays per worker, unless a step of that size takes long enough (train: ~10 s on 128 cores) that a smaller
+        # one still dwarfs the process-pool overhead: then as few rays as keep a step above ~1.5 s, so that a run with many
+        # steps (--steps 20 --warmup 5) still ends within the budget instead of 25 x 10 s.
+        floor = int(min(16, max(1, -(-16 * 1.5 // max(sec, 1e-3)))))
+        rpw = int(min(64, max(floor, 16 * per_step / max(sec, 1e-3))))
     rays, sec = run(rpw, a.steps, max(a.warmup, 1))
     what = ("prune pass + forward + loss + autograd backward per worker, one dense Adam over all parameters with all threads"
             if train else "encode + MLPs + composite per worker")

@@ -139,3 +139,57 @@ def test_dropin_maps_reference_import_paths():
         for k in list(sys.modules):
             if k.startswith(("humanrf.", "actorshq.")) or k in ("humanrf", "actorshq"):
                 del sys.modules[k]
+
+
+def test_bench_reads_roofline_evidence_of_the_default_kernels():
+    """bench.py fills roofline.traffic and the unit percentages from the newest committed `ncu --set full` export that holds the
+    kernel it names: the default scatter generation for the train line, the fused forward for the render line."""
+    import sys
+
+    sys.path.insert(0, str(ROOT))
+    import bench
+
+    for kernel in ("grid_scatter_v3_kernel", "field_forward_kernel"):
+        prof = bench.committed_ncu(kernel)
+        assert prof is not None and kernel in prof["kernel_name"], kernel
+        assert prof["source"].startswith("profiles/r2") and prof["source"].endswith("_raw.csv")
+        assert prof["traffic"] > 1e6 and 0 < prof["issue_slots_pct"] <= 100 and 0 < prof["l2_pct"] <= 100
+    assert bench.committed_ncu("no_such_kernel") is None
+
+
+def test_reference_arm_line_follows_the_bench_contract(monkeypatch, capsys):
+    """`bench.py --impl reference`: one JSON line with the b200 arm's metric / unit, impl, cpu_baseline (kind, cores, sample) and an
+    e2e that repeats the value with zero copies.  (The CPU oracle run itself is replaced by a stub: it takes minutes.)"""
+    import argparse
+    import json
+    import sys
+
+    sys.path.insert(0, str(ROOT))
+    import bench
+
+    monkeypatch.setattr(bench, "cpu_oracle_rate", lambda mode, steps, warmup, budget_s: (
+        123.0, 8, "stub sample", {"seconds_per_step": 2.0, "rays_per_step": 246}))
+    monkeypatch.setattr(bench, "dist_info", lambda: (0, 1, 0))
+    bench.run_reference(argparse.Namespace(mode="train", steps=3, warmup=1, gpus=1))
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == bench.METRIC["train"] and line["unit"] == "rays/s"
+    assert line["value"] == 123.0 and line["higher_is_better"] is True and line["steps"] == 3 and line["warmup"] == 1
+    assert line["cpu_baseline"] == {"value": 123.0, "unit": "rays/s", "cores": 8, "kind": "port", "sample": "stub sample"}
+    assert line["e2e"] == {"value": 123.0, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # ranks other than 0 print nothing
+    monkeypatch.setattr(bench, "dist_info", lambda: (1, 2, 1))
+    bench.run_reference(argparse.Namespace(mode="train", steps=3, warmup=1, gpus=2))
+    assert capsys.readouterr().out.strip() == ""
+
+
+def test_cpu_oracle_bench_runs_a_tiny_train_step():
+    """oracle/cpu_bench.py end to end at one ray per worker (two workers): prune pass, forward, loss, autograd backward, Adam."""
+    import json
+    import subprocess
+    import sys
+
+    out = subprocess.run([sys.executable, str(ROOT / "oracle" / "cpu_bench.py"), "--mode", "train", "--rays-per-worker", "1",
+                          "--workers", "2", "--steps", "1", "--warmup", "1", "--samples-per-ray", "64"],
+                         capture_output=True, text=True, check=True, timeout=600).stdout.strip().splitlines()[-1]
+    r = json.loads(out)
+    assert r["rays_per_step"] == 2 and r["cores"] == 2 and r["rays_per_s"] > 0 and "Adam" in r["sample"]
